@@ -1,0 +1,89 @@
+"""Oracle vs the golden vectors recorded from the reference's own Python files (tools/gen_golden.py).
+
+This is the parity pin of the oracle: the vectors come from /root/reference/utils/depth_operations.py,
+utils/dense_image_warp.py and m4depth_network.py executed unmodified on tools/tf_shim.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+T = torch.from_numpy
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def cam_of(g):
+    return {"f": T(g["cam_f"]), "c": T(g["cam_c"])}
+
+
+@pytest.mark.parametrize("case", ["l2_kitti", "l1_midair", "l4_tartan", "l6_kitti"])
+@pytest.mark.parametrize("branch", ["gather", "bp"])
+def test_pscv_matches_reference(golden_dir, case, branch):
+    g = load(golden_dir, f"pscv_{case}.npz")
+    cv, pd = oracle.get_parallax_sweeping_cv(T(g["c1"]), T(g["c2"]), T(g["para_prev_t"]), T(g["para_prev_l"]),
+                                             T(g["rot"]), T(g["trans"]), cam_of(g), 4, nbre_cuts=int(g["cuts"]),
+                                             use_cuda_backproject=(branch == "bp"))
+    # same primitive arithmetic in the same order -> bit-exact
+    assert np.array_equal(cv.numpy(), g["cv_" + branch])
+    assert np.array_equal(pd.numpy(), g["prev_disp_" + branch])
+
+
+@pytest.mark.parametrize("case", ["l2_kitti", "l4_tartan"])
+def test_pscv_branches_agree(golden_dir, case):
+    """python-gather and BackProject branches give the same values."""
+    g = load(golden_dir, f"pscv_{case}.npz")
+    np.testing.assert_allclose(g["prev_disp_gather"], g["prev_disp_bp"], rtol=1e-5, atol=1e-6)
+    # cv is fp16-quantised: allow 1 fp16 ulp of the largest magnitude
+    assert np.max(np.abs(g["cv_gather"] - g["cv_bp"])) <= 2.0 ** -14
+
+
+@pytest.mark.parametrize("case", ["l2", "l6"])
+def test_sncv_matches_reference(golden_dir, case):
+    g = load(golden_dir, f"sncv_{case}.npz")
+    out = oracle.cost_volume(T(g["f"]), T(g["f"]), 3, nbre_cuts=int(g["cuts"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", ["kitti", "tartan"])
+def test_geometry_matches_reference(golden_dir, case):
+    g = load(golden_dir, f"geom_{case}.npz")
+    cam = cam_of(g)
+    rot, trans = T(g["rot"]), T(g["trans"])
+    assert np.array_equal(oracle.get_rot_mat(rot).numpy(), g["rot_mat"])
+    assert np.array_equal(oracle.prev_d2para(T(g["depth"]), rot, trans, cam).numpy(), g["prev_d2para"])
+    assert np.array_equal(oracle.parallax2depth(T(g["para"]), rot, trans, cam).numpy(), g["parallax2depth"])
+    assert np.array_equal(oracle.depth2parallax(T(g["depth"]), rot, trans, cam).numpy(), g["depth2parallax"])
+    assert np.array_equal(oracle.dense_image_warp(T(g["img"]), T(g["flow"]), False).numpy(), g["warp_gather"])
+    assert np.array_equal(oracle.dense_image_warp(T(g["img"]), T(g["flow"]), True).numpy(), g["warp_bp"])
+
+
+def test_domain_normalization_matches_reference(golden_dir):
+    g = load(golden_dir, "dn.npz")
+    out = oracle.DomainNormalization(T(g["scale"]), T(g["bias"]))(T(g["x"]))
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", ["cfg1", "cfg1_bp", "odd"])
+def test_model_matches_reference(golden_dir, case):
+    g = load(golden_dir, f"model_{case}.npz")
+    nl = int(g["nbre_levels"])
+    w = oracle.init_weights(nl, seed=int(g["weights_seed"]), bias_std=0.05, dn_random=True)
+    model = oracle.M4Depth(w, nbre_levels=nl, pscv_kwargs={"use_cuda_backproject": bool(g["backproject"])})
+    cam = cam_of(g)
+    t = 0
+    while f"rgb_{t}" in g:
+        b = g[f"rgb_{t}"].shape[0]
+        sample = {"RGB_im": T(g[f"rgb_{t}"]), "rot": T(g[f"rot_{t}"]), "trans": T(g[f"trans_{t}"]),
+                  "new_traj": torch.tensor([t == 0] * b)}
+        out = model([[sample], cam])
+        np.testing.assert_allclose(out["depth"].numpy(), g[f"depth_{t}"], rtol=1e-4, atol=1e-5)  # depth=(s/rho-tz)/alpha cancels near 0: atol
+        for li, lvl in enumerate(model.d_estimator.levels):
+            np.testing.assert_allclose(lvl.depth_prev_t.numpy(), g[f"state_depth_{t}_l{li + 1}"], rtol=1e-4, atol=1e-5)
+        t += 1
+    assert t >= 2
