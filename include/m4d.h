@@ -1,0 +1,178 @@
+/*
+ * m4d.h - C ABI of libm4d.so, the B200-native (sm_100a) implementation of M4Depth's per-frame
+ * parallax-inference hot path.
+ *
+ * This is the drop-in boundary: every entry point below is what a binding for the reference's
+ * operator / function would call (TF custom-op shim, ctypes, cgo ...).  Plain pointers and sizes only.
+ * Reference citations are relative to the M4Depth repository root.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  All tensors are dense NHWC fp32
+ *     exactly like the reference's tensors; "pix_stride" arguments (in floats) let a kernel write its
+ *     channels straight into a wider buffer (the refiner input) instead of a compact tensor.
+ *   - The caller owns every buffer.  The library never allocates device memory, keeps no hidden state,
+ *     never synchronises and enqueues everything (including zero fills) on the caller's stream, so every
+ *     call is CUDA-graph capturable and re-entrant.  (The reference memsets on the legacy default stream
+ *     and exit(-1)s on launch errors: cuda_backproject/backproject_op_gpu.cu.cc:91-100.)
+ *   - Return value: 0 on success, a negative M4D_E* code otherwise; m4d_last_error_string() returns a
+ *     thread-local description of the last failure.  Nothing ever calls exit().
+ *   - stream is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - rot is [b, rot_dim] with rot_dim 4 = quaternion (w,x,y,z), 3 = small angles (x,y,z)
+ *     (utils/depth_operations.py:18-53); trans is [b,3]; cam_f / cam_c are [b,2] = (fx,fy) / (cx,cy) ALREADY
+ *     divided by 2^level as DepthEstimatorPyramid.call does (m4depth_network.py:300-302).
+ *   - Floating-point contract: geometry is evaluated with one rounded fp32 operation per reference TF op
+ *     (no FMA contraction, IEEE division and square root) so the integer tap grids x0,x1,y0,y1 are
+ *     bit-identical to the oracle's; see DESIGN.md "Numerics".
+ */
+#ifndef M4D_H_
+#define M4D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M4D_OK 0
+#define M4D_EINVAL (-1)   /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define M4D_ECUDA (-2)    /* CUDA runtime / launch error; see m4d_last_error_string() */
+#define M4D_ENOTSUP (-3)  /* shape outside what the kernel family supports */
+
+#define M4D_ABI_VERSION 1
+
+int m4d_abi_version(void);
+const char* m4d_last_error_string(void);
+/* Number of kernels launched by this library since load (all threads); used by bench.py for "gpu_launches". */
+uint64_t m4d_launch_count(void);
+
+/* ---- L0: BackProject op ------------------------------------------------------------------------
+ * Replaces BackProjectForwardLauncher (cuda_backproject/backproject_op_gpu.h:17-18, kernel
+ * backproject_op_gpu.cu.cc:19-79) = TF op "BackProject" (backproject_op.cc:32-35).
+ * dim = {B,H,W,S,F,C}; input [B,H,W,F,C]; coords [B,H,W,S,F,2] (x,y); out [B,H,W,S,F,C].
+ * out is fully written (zero where the coordinate is outside [0,W-1]x[0,H-1] or NaN); no separate memset.
+ * idx_dbg (nullable) int32 [B,H,W,S,F,4] receives the tap grid x0,x1,y0,y1 (-1 where outside). */
+int m4d_backproject_fwd(const float* input, const float* coords, const int32_t dim[6], float* out,
+                        int32_t* idx_dbg, void* stream);
+
+/* ---- L1: dense_image_warp (utils/dense_image_warp.py:195-268, BackProject branch :246-253) -------
+ * image [b,h,w,c], flow [b,h,w,2] (row, col); query = grid + flow, clipped to the image. */
+int m4d_dense_image_warp(const float* image, const float* flow, int b, int h, int w, int c, float* out,
+                         void* stream);
+
+/* ---- L2: geometry (utils/depth_operations.py) ---------------------------------------------------*/
+/* get_rot_mat :18-53  -> out [b,9] row-major */
+int m4d_get_rot_mat(const float* rot, int b, int rot_dim, float* out, void* stream);
+/* prev_d2para :196-215 ; parallax2depth :140-166 ; depth2parallax :168-194 ; maps are [b,h,w,1] */
+int m4d_prev_d2para(const float* prev_d, const float* rot, int rot_dim, const float* trans, const float* cam_f,
+                    const float* cam_c, int b, int h, int w, float* out, void* stream);
+int m4d_parallax2depth(const float* para, const float* rot, int rot_dim, const float* trans, const float* cam_f,
+                       const float* cam_c, int b, int h, int w, float* out, void* stream);
+int m4d_depth2parallax(const float* depth, const float* rot, int rot_dim, const float* trans, const float* cam_f,
+                       const float* cam_c, int b, int h, int w, float* out, void* stream);
+
+/* ---- L2: fused backproject + parallax-sweeping cost volume --------------------------------------
+ * Replaces get_parallax_sweeping_cv (utils/depth_operations.py:223-281) together with the
+ * tile_in_batch copies (:217-221, :267-268), dense_image_warp and BackProject it calls, and the fp16
+ * correlate (:276-278).  K = 2*search_range+1.
+ *   c1, c2        [b,h,w,c]   current / previous (already group-normalised) feature maps
+ *   para_prev_t   [b,h,w]     (disp_prev_t) sampled alongside c2
+ *   para_prev_l   [b,h,w]     (disp) the parallax the sweep is centred on
+ *   cv            [b,h,w,cuts*K] cut-major (channel = cut*K + k), row stride cv_pix_stride floats
+ *   prev_disp     nullable, [b,h,w,K] row stride pd_pix_stride floats
+ *   centre_log    nullable, receives log(prev_disp[...,search_range] * centre_log_scale) at
+ *                 centre_log[pixel*centre_log_pix_stride] (m4depth_network.py:238); with prev_disp NULL
+ *                 only this consumed channel is produced
+ *   idx_dbg       nullable int32 [b,h,w,K,4] = x0,x1,y0,y1 of the BackProject convention (-1 outside)
+ * fp16 contract: products of fp16-rounded operands rounded to fp16, summed in fp32, /n, rounded once to fp16. */
+int m4d_pscv_fused_fwd(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
+                       const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
+                       int b, int h, int w, int c, int cuts, int search_range,
+                       float* cv, int cv_pix_stride, float* prev_disp, int pd_pix_stride,
+                       float* centre_log, int centre_log_pix_stride, float centre_log_scale,
+                       int32_t* idx_dbg, void* stream);
+
+/* Bilinear-sampling convention of the warp inside the PSCV.  The reference has two code paths for the same op:
+ *   GATHER  utils/dense_image_warp.py:127-190,255-259 - what runs on the TF CPU path and whenever backproject.so is
+ *           not found (the default: make.sh writes the .so where dense_image_warp.py:38 does not look);
+ *   BP      dense_image_warp.py:246-253 + backproject_op_gpu.cu.cc:44-76 with every product / sum rounded separately;
+ *   BP_FMA  the same kernel expression (:74) as nvcc compiles it by default (mul, fma, fma, fma) - the arithmetic of
+ *           the reference's own GPU binary.
+ * m4d_pscv_fused_fwd uses GATHER; m4d_pscv_fused_fwd_ex takes the convention explicitly. */
+#define M4D_INTERP_GATHER 0
+#define M4D_INTERP_BP 1
+#define M4D_INTERP_BP_FMA 2
+int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
+                          const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
+                          int b, int h, int w, int c, int cuts, int search_range,
+                          float* cv, int cv_pix_stride, float* prev_disp, int pd_pix_stride,
+                          float* centre_log, int centre_log_pix_stride, float centre_log_scale,
+                          int32_t* idx_dbg, int interp, void* stream);
+
+/* ---- L2: spatial self-correlation cost volume ---------------------------------------------------
+ * Replaces cost_volume (utils/depth_operations.py:283-313), dilation 1.
+ * out[b,y,x,(dy*(2r+1)+dx)*cuts + k] = leaky_0.1(mean_{j in group k} c1[b,y,x,j]*c2pad[b,y+dy-r,x+dx-r,j]) */
+int m4d_sncv_fwd(const float* c1, const float* c2, int b, int h, int w, int c, int cuts, int search_range,
+                 float* out, int out_pix_stride, void* stream);
+
+/* ---- L3: layer pieces (m4depth_network.py) ------------------------------------------------------*/
+/* tf.linalg.normalize per feature group, no epsilon (:180,185-186).  in/out [b,h,w,c] (may alias). */
+int m4d_group_l2norm(const float* in, int npix, int c, int cuts, float* out, void* stream);
+
+/* DomainNormalization.call (:44-48).  x [b,h,w,c] (c <= 64); stats_ws: caller-provided workspace of
+ * 2*b*c doubles (need not be initialised); leaky_alpha != 1 additionally applies leaky_relu (:84). */
+int m4d_domain_norm(const float* x, int b, int h, int w, int c, const float* scale, const float* bias,
+                    float leaky_alpha, double* stats_ws, float* out, void* stream);
+
+/* Keras Conv2D(3x3, padding='same') + bias + optional leaky_relu (:63-72,104-114; TF SAME padding rule).
+ * x [b,h,w,cin] with row stride x_pix_stride (>= cin); kernel HWIO [3,3,cin,cout]; y [b,oh,ow,cout] with row
+ * stride y_pix_stride, oh = ceil(h/stride).  leaky_alpha = 1 means no activation.
+ * algo: 0 = auto, 1 = FFMA direct, 2 = tcgen05 3xTF32 (M4D_ENOTSUP if the shape does not fit). */
+int m4d_conv3x3_nhwc(const float* x, int x_pix_stride, const float* kernel_hwio, const float* bias,
+                     int b, int h, int w, int cin, int cout, int stride, float leaky_alpha,
+                     float* y, int y_pix_stride, int algo, void* stream);
+
+/* tf.compat.v1.image.resize_bilinear, align_corners=False, no half-pixel (:202-204); post_scale multiplies the
+ * result (parallax is doubled after resizing).  in [b,ih,iw,c] -> out [b,oh,ow,c] with row stride. */
+int m4d_resize_bilinear_legacy(const float* in, int b, int ih, int iw, int c, int oh, int ow, float post_scale,
+                               float* out, int out_pix_stride, void* stream);
+/* tf.image.resize(method=NEAREST) (:368-369) */
+int m4d_resize_nearest(const float* in, int b, int ih, int iw, int c, int oh, int ow, float* out, void* stream);
+
+/* Fused level prologue (:196-204, 218, 224, 227): from the previous (coarser) level's estimate
+ * {other [b,ih,iw,4], parallax, depth [b,ih,iw]} (all NULL for the deepest level -> 1 / 1000 / 0) produce
+ *   para_prev_l, depth_prev_l [b,h,w]; other_prev_l -> x_in[..., ch_other..ch_other+3];
+ *   log(para_prev_l * log_scale) -> x_in[..., ch_logpara]; and, when state_depth != NULL,
+ *   para_prev_t = prev_d2para(state_depth) [b,h,w].
+ * x_in may be NULL (new-trajectory frame: only the pass-through values are needed); ch_other < 0 skips the
+ * "other" channels (level_memory ablation); other_out (nullable) receives other_prev_l compactly [b,h,w,4]. */
+int m4d_level_prologue(const float* prev_other, const float* prev_para, const float* prev_depth, int ih, int iw,
+                       const float* state_depth, const float* rot, int rot_dim, const float* trans,
+                       const float* cam_f, const float* cam_c, int b, int h, int w,
+                       float* para_prev_l, float* depth_prev_l, float* other_out, float* para_prev_t,
+                       float* x_in, int x_pix_stride, int ch_logpara, int ch_other, float log_scale, void* stream);
+
+/* Fused level epilogue (:247-260): refiner output r [b,h,w,5] (row stride r_pix_stride) ->
+ * parallax = exp(clip(r0,-7,7)) * inv_scale, depth = parallax2depth(parallax), other = r[1:5];
+ * depth_state (nullable) receives a second copy of depth: what the level stores as depth_prev_t (:260). */
+int m4d_level_epilogue(const float* r, int r_pix_stride, const float* rot, int rot_dim, const float* trans,
+                       const float* cam_f, const float* cam_c, int b, int h, int w, float inv_scale,
+                       float* parallax, float* depth, float* other, float* depth_state, void* stream);
+
+/* Per-level intrinsics of DepthEstimatorPyramid.call (:300-302): out_f[l], out_c[l] ([nlevels,b,2]) = cam / 2^(l+1),
+ * l = 0 .. nlevels-1 (exact: power-of-two divisions). */
+int m4d_camera_pyramid(const float* cam_f, const float* cam_c, int b, int nlevels, float* out_f, float* out_c,
+                       void* stream);
+
+/* fill(n floats) on the stream (state reset: depth_prev_t <- 1000, m4depth_network.py:209) */
+int m4d_fill(float* p, int64_t n, float value, void* stream);
+
+/* ---- metrics (metrics.py:1-64 + clipping m4depth_network.py:465-467) ----------------------------
+ * gt, est [n] -> out[7] = AbsRel, SqRel, RMSE, RMSE_log, Delta1, Delta2, Delta3 for this batch
+ * (one keras Mean.update_state sample each).  ws: 16 doubles of caller workspace. */
+int m4d_depth_metrics(const float* gt, const float* est, int64_t n, float max_d, double* ws, float* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M4D_H_ */

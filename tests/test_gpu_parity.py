@@ -1,0 +1,447 @@
+"""GPU parity tests: libm4d (through the C ABI via the Python mirror) vs the CPU oracle and the golden vectors.
+
+Tolerances (DESIGN.md "Numerics"):
+  * integer tap grids of the BackProject convention: bit-exact;
+  * PSCV cv (fp16-quantised) and prev_disp, geometry maps, warps: bit-exact against the oracle branch that uses the
+    same bilinear convention (the kernels evaluate the reference's op sequence with one rounding per op);
+  * fp32 reductions whose order is not defined by the reference (SNCV mean, DN statistics, convolutions):
+    1e-5 relative to the tensor scale (north_star allows 1e-4);
+  * whole model: the statistical bound of tests/test_oracle_golden.py::check_depth.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+
+
+def _m4d():
+    import m4depth_b200
+    return m4depth_b200
+
+
+def load(golden_dir, name):
+    return dict(np.load(os.path.join(golden_dir, name)))
+
+
+def cu(x):
+    return (T(x) if isinstance(x, np.ndarray) else x).cuda().contiguous()
+
+
+def cam_of(g, dev=True):
+    f, c = T(g["cam_f"]), T(g["cam_c"])
+    return {"f": f.cuda(), "c": c.cuda()} if dev else {"f": f, "c": c}
+
+
+def camera_for(kind, b, h, w):
+    if kind == "kitti":
+        f, c = (0.580948 * w, 1.924101 * h), (0.490788 * w, 0.460944 * h)
+    elif kind == "midair":
+        f, c = (0.5 * w, 0.5 * h), (0.5 * w, 0.5 * h)
+    else:
+        f, c = (0.5 * w, 2.0 / 3.0 * h), (0.5 * w, 0.5 * h)
+    return {"f": torch.tensor([f] * b, dtype=torch.float32), "c": torch.tensor([c] * b, dtype=torch.float32)}
+
+
+def motion(g, b):
+    rot = torch.cat([torch.ones(b, 1), 0.01 * torch.randn(b, 3, generator=g)], 1)
+    rot = rot / rot.norm(dim=1, keepdim=True)
+    trans = torch.tensor([0.0, 0.0, 1.0]) + torch.randn(b, 3, generator=g) * torch.tensor([0.05, 0.05, 0.3])
+    return rot, trans
+
+
+def pscv_inputs(seed, b, h, w, c, cuts, kind):
+    g = torch.Generator().manual_seed(seed)
+    cam = camera_for(kind, b, h, w)
+    rot, trans = motion(g, b)
+    lk = lambda t: torch.where(t >= 0, t, 0.1 * t)
+    c1 = oracle.group_l2_normalize(lk(torch.randn(b, h, w, c, generator=g)), cuts)
+    c2 = oracle.group_l2_normalize(lk(torch.randn(b, h, w, c, generator=g)), cuts)
+    para_l = torch.exp(torch.rand(b, h, w, 1, generator=g) * (np.log(16) - np.log(0.5)) + np.log(0.5))
+    para_t = torch.exp(torch.rand(b, h, w, 1, generator=g) * (np.log(16) - np.log(0.05)) + np.log(0.05))
+    return c1, c2, para_t, para_l, rot, trans, cam
+
+
+def dev_cam(cam):
+    return {"f": cam["f"].cuda(), "c": cam["c"].cuda()}
+
+
+# ------------------------------------------------------------------------------------------ library
+def test_library_loaded_and_counts_launches():
+    m = _m4d()
+    assert m._lib.ABI_VERSION == 1
+    n0 = m.launch_count()
+    x = torch.zeros(8, device="cuda")
+    m._lib.check(m._lib.lib.m4d_fill(x.data_ptr(), 8, 3.0, m._lib.stream()))
+    torch.cuda.synchronize()
+    assert m.launch_count() == n0 + 1
+    assert torch.all(x == 3.0)
+
+
+def test_errors_are_returned_not_fatal():
+    m = _m4d()
+    rc = m._lib.lib.m4d_fill(None, 8, 1.0, None)
+    assert rc == -1 and "null" in m._lib.last_error()
+    with pytest.raises(m.M4DError):
+        m.utils.cost_volume(torch.zeros(1, 4, 4, 6, device="cuda"), torch.zeros(1, 4, 4, 6, device="cuda"), 3, nbre_cuts=1)
+    with pytest.raises(m.M4DError):
+        m.utils.cost_volume(torch.zeros(1, 4, 4, 8), torch.zeros(1, 4, 4, 8), 3)      # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        m.utils.get_rot_mat(torch.zeros(2, 5, device="cuda"))
+
+
+# ------------------------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("case", ["l2_kitti", "l1_midair", "l4_tartan", "l6_kitti"])
+@pytest.mark.parametrize("branch", ["gather", "bp"])
+def test_pscv_golden(golden_dir, case, branch):
+    m = _m4d()
+    g = load(golden_dir, f"pscv_{case}.npz")
+    interp = m.INTERP_GATHER if branch == "gather" else m.INTERP_BP
+    cv, pd = m.utils.get_parallax_sweeping_cv(cu(g["c1"]), cu(g["c2"]), cu(g["para_prev_t"]), cu(g["para_prev_l"]),
+                                              cu(g["rot"]), cu(g["trans"]), cam_of(g), 4, nbre_cuts=int(g["cuts"]),
+                                              interp=interp)
+    assert np.array_equal(pd.cpu().numpy(), g["prev_disp_" + branch])
+    assert np.array_equal(cv.cpu().numpy(), g["cv_" + branch])
+
+
+@pytest.mark.parametrize("case", ["l2", "l6"])
+def test_sncv_golden(golden_dir, case):
+    m = _m4d()
+    g = load(golden_dir, f"sncv_{case}.npz")
+    f = cu(g["f"])
+    out = m.utils.cost_volume(f, f, 3, nbre_cuts=int(g["cuts"]))
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("case", ["kitti", "tartan"])
+def test_geometry_golden(golden_dir, case):
+    m = _m4d()
+    g = load(golden_dir, f"geom_{case}.npz")
+    cam = cam_of(g)
+    rot, trans = cu(g["rot"]), cu(g["trans"])
+    assert np.array_equal(m.utils.get_rot_mat(rot).cpu().numpy(), g["rot_mat"])
+    assert np.array_equal(m.utils.prev_d2para(cu(g["depth"]), rot, trans, cam).cpu().numpy(), g["prev_d2para"])
+    assert np.array_equal(m.utils.parallax2depth(cu(g["para"]), rot, trans, cam).cpu().numpy(), g["parallax2depth"])
+    assert np.array_equal(m.utils.depth2parallax(cu(g["depth"]), rot, trans, cam).cpu().numpy(), g["depth2parallax"])
+    # dense_image_warp: the library implements the BackProject branch with the compiled kernel's FMA contraction;
+    # against the separately-rounded restatement that is <= 2 ulp of the largest term
+    w = m.utils.dense_image_warp(cu(g["img"]), cu(g["flow"])).cpu().numpy()
+    np.testing.assert_allclose(w, g["warp_bp"], rtol=0, atol=4e-7 * np.abs(g["img"]).max())
+    np.testing.assert_allclose(w, g["warp_gather"], rtol=0, atol=2e-6 * np.abs(g["img"]).max())
+
+
+def test_domain_normalization_golden(golden_dir):
+    m = _m4d()
+    g = load(golden_dir, "dn.npz")
+    dn = m.DomainNormalization()
+    dn.scale, dn.bias = cu(g["scale"]), cu(g["bias"])
+    out = dn(cu(g["x"]))
+    np.testing.assert_allclose(out.cpu().numpy(), g["out"], rtol=1e-5, atol=1e-6)
+
+
+def check_depth(got, want, frame):
+    """Frame 0 (new-trajectory pass-through) must match to 1e-4 everywhere.  From frame 1 on the fp16 stage of the
+    PSCV amplifies legitimate 1e-7 fp32 summation-order differences (convolutions, normalisations) into isolated
+    fp16-ulp flips, so the bound is the statistical one of tests/test_oracle_golden.py (DESIGN.md "Numerics")."""
+    err = np.abs(got - want) / (np.abs(want) + 0.1)
+    if frame == 0:
+        assert err.max() <= 1e-4, err.max()
+    else:
+        assert np.median(err) <= 1e-5 and np.percentile(err, 99) <= 1e-3 and err.max() <= 1e-2, \
+            (np.median(err), np.percentile(err, 99), err.max())
+
+
+@pytest.mark.parametrize("case", ["cfg1", "cfg1_bp", "odd"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_model_golden(golden_dir, case, graph):
+    """BASELINE config 1 (128x128, 3 levels, 2 frames) and an odd-sized 6-level case, frame by frame."""
+    m = _m4d()
+    g = load(golden_dir, f"model_{case}.npz")
+    nl = int(g["nbre_levels"])
+    model = m.M4Depth(nbre_levels=nl, use_cuda_graph=graph)
+    model.load_weights(oracle.init_weights(nl, seed=int(g["weights_seed"]), bias_std=0.05, dn_random=True))
+    model.set_interp(m.INTERP_BP if bool(g["backproject"]) else m.INTERP_GATHER)
+    cam = cam_of(g)
+    t = 0
+    while f"rgb_{t}" in g:
+        b = g[f"rgb_{t}"].shape[0]
+        sample = {"RGB_im": cu(g[f"rgb_{t}"]), "rot": cu(g[f"rot_{t}"]), "trans": cu(g[f"trans_{t}"]),
+                  "new_traj": [t == 0] * b}
+        out = model([[sample], cam])
+        check_depth(out["depth"].cpu().numpy(), g[f"depth_{t}"], t)
+        for li, lvl in enumerate(model.d_estimator.levels):
+            check_depth(lvl.depth_prev_t.cpu().numpy(), g[f"state_depth_{t}_l{li + 1}"], t)
+        t += 1
+    assert t >= 2
+
+
+# ------------------------------------------------------------------- seeded inputs vs the oracle, all level shapes
+LEVEL_SHAPES = [  # (name, b, h, w, c, cuts, camera kind): the level shapes of BASELINE configs 1-5
+    ("cfg1_l1", 1, 64, 64, 16, 1, "midair"), ("cfg1_l3", 1, 16, 16, 64, 2, "midair"),
+    ("cfg2_l2", 1, 96, 96, 32, 2, "midair"), ("cfg2_l4", 1, 24, 24, 96, 4, "midair"),
+    ("cfg3_l3", 2, 48, 160, 64, 2, "kitti"), ("cfg3_l5", 2, 12, 40, 128, 4, "kitti"),
+    ("cfg3_l6", 8, 6, 20, 192, 8, "kitti"), ("cfg5_l6", 2, 8, 10, 192, 8, "tartan"),
+    ("cfg5_l5", 1, 15, 20, 128, 4, "tartan"), ("ragged", 3, 5, 7, 32, 2, "kitti"),
+]
+
+
+@pytest.mark.parametrize("shape", LEVEL_SHAPES, ids=[s[0] for s in LEVEL_SHAPES])
+@pytest.mark.parametrize("interp", ["gather", "bp"])
+def test_pscv_vs_oracle(shape, interp):
+    m = _m4d()
+    _, b, h, w, c, cuts, kind = shape
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(100 + h * w + c, b, h, w, c, cuts, kind)
+    want_cv, want_pd = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts,
+                                                       use_cuda_backproject=(interp == "bp"))
+    cv, pd, idx = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4,
+                                                   nbre_cuts=cuts, interp=m.INTERP_BP if interp == "bp" else m.INTERP_GATHER,
+                                                   return_index_grids=True)
+    # integer index grids of the backproject op: bit-exact
+    qy, qx = oracle.pscv_query_points(pl, rot, trans, cam, 4)
+    qx = torch.minimum(torch.maximum(qx, torch.zeros(())), torch.tensor(float(w - 1)))
+    qy = torch.minimum(torch.maximum(qy, torch.zeros(())), torch.tensor(float(h - 1)))
+    x0, x1, y0, y1, _ = oracle.back_project_index_grids(torch.stack((qx, qy), dim=-1), h, w)
+    want_idx = torch.stack((x0, x1, y0, y1), dim=-1).permute(1, 2, 3, 0, 4)      # [K,b,h,w,4] -> [b,h,w,K,4]
+    assert torch.equal(idx.cpu(), want_idx)
+    assert torch.equal(pd.cpu(), want_pd)
+    assert torch.equal(cv.cpu(), want_cv)
+
+
+def test_pscv_bp_fma_close_to_bp():
+    """BP_FMA (the reference GPU binary's contraction) vs separately rounded BP: fp32 values within 2 ulp of the
+    largest term, fp16-quantised cv within one fp16 ulp and equal almost everywhere."""
+    m = _m4d()
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(7, 2, 24, 80, 96, 4, "kitti")
+    args = (cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4)
+    cv_a, pd_a = m.utils.get_parallax_sweeping_cv(*args, nbre_cuts=4, interp=m.INTERP_BP)
+    cv_b, pd_b = m.utils.get_parallax_sweeping_cv(*args, nbre_cuts=4, interp=m.INTERP_BP_FMA)
+    assert torch.allclose(pd_a, pd_b, rtol=0, atol=4e-7 * float(pt.max()))
+    d = (cv_a - cv_b).abs()
+    assert float(d.max()) <= 2.0 ** -11 * float(cv_a.abs().max())
+    assert float((d > 0).float().mean()) < 0.02
+
+
+def test_pscv_unnormalised_features_within_one_fp16_ulp():
+    """Features that are NOT group-normalised (ablation): partial sums are no longer exact in fp32, so the kernel's
+    summation tree may differ from the oracle's channel-order sum by one rounding of the final fp16 value."""
+    m = _m4d()
+    g = torch.Generator().manual_seed(3)
+    b, h, w, c, cuts = 1, 12, 40, 32, 2
+    c1 = torch.randn(b, h, w, c, generator=g) * 3
+    c2 = torch.randn(b, h, w, c, generator=g) * 3
+    _, _, pt, pl, rot, trans, cam = pscv_inputs(4, b, h, w, c, cuts, "kitti")
+    want_cv, _ = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, use_cuda_backproject=False)
+    cv, _ = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4, nbre_cuts=cuts)
+    d = (cv.cpu() - want_cv).abs()
+    assert float((d / want_cv.abs().clamp(min=2.0 ** -14)).max()) <= 2.0 ** -10
+    assert float((d > 0).float().mean()) < 0.01
+
+
+def test_pscv_strided_outputs_and_centre_log():
+    """The fused-pipeline form: cv written into a wider refiner-input buffer, only log(centre prev_disp * scale) kept."""
+    m = _m4d()
+    L = m._lib
+    b, h, w, c, cuts = 2, 12, 40, 32, 2
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(9, b, h, w, c, cuts, "kitti")
+    dc = dev_cam(cam)
+    cv, pd = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dc, 4, nbre_cuts=cuts)
+    xs = 124
+    x_in = torch.full((b, h, w, xs), -5.0, device="cuda")
+    d = [cu(t) for t in (c1, c2, pt, pl, rot, trans)]
+    L.check(L.lib.m4d_pscv_fused_fwd(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), d[3].data_ptr(), d[4].data_ptr(), 4,
+                                     d[5].data_ptr(), dc["f"].data_ptr(), dc["c"].data_ptr(), b, h, w, c, cuts, 4,
+                                     x_in.data_ptr() + 4 * 3, xs, None, 0, x_in.data_ptr() + 4 * 121, xs, 0.5, None, L.stream()))
+    assert torch.equal(x_in[..., 3:21], cv)
+    assert torch.allclose(x_in[..., 121], torch.log(pd[..., 4] * 0.5), rtol=1e-6, atol=1e-6)
+    untouched = torch.ones(xs, dtype=torch.bool)
+    untouched[3:21] = False
+    untouched[121] = False
+    assert torch.all(x_in[..., untouched.cuda()] == -5.0)
+
+
+def test_pscv_edge_cases():
+    """Parallax far outside the image (clamped taps), negative hypotheses (collapse onto p), tiny maps."""
+    m = _m4d()
+    b, h, w, c, cuts = 2, 2, 3, 32, 2
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(21, b, h, w, c, cuts, "tartan")
+    pl = pl * 0 + torch.tensor([0.3, 500.0]).view(2, 1, 1, 1)
+    for interp, flag in ((m.INTERP_GATHER, False), (m.INTERP_BP, True)):
+        want_cv, want_pd = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, use_cuda_backproject=flag)
+        cv, pd = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4,
+                                                  nbre_cuts=cuts, interp=interp)
+        assert torch.equal(cv.cpu(), want_cv) and torch.equal(pd.cpu(), want_pd)
+
+
+@pytest.mark.parametrize("shape", LEVEL_SHAPES, ids=[s[0] for s in LEVEL_SHAPES])
+def test_sncv_vs_oracle(shape):
+    m = _m4d()
+    _, b, h, w, c, cuts, _ = shape
+    g = torch.Generator().manual_seed(h * w + c)
+    f = oracle.group_l2_normalize(torch.randn(b, h, w, c, generator=g), cuts)
+    f2 = oracle.group_l2_normalize(torch.randn(b, h, w, c, generator=g), cuts)
+    want = oracle.cost_volume(f, f2, 3, nbre_cuts=cuts)
+    out = m.utils.cost_volume(cu(f), cu(f2), 3, nbre_cuts=cuts)
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_backproject_op_vs_oracle():
+    """General BackProject signature (S, F > 1), out-of-range and NaN coordinates, index grids bit-exact."""
+    m = _m4d()
+    g = torch.Generator().manual_seed(5)
+    B, H, W, S, Fd, C = 2, 7, 9, 3, 2, 5
+    inp = torch.randn(B, H, W, Fd, C, generator=g)
+    coords = torch.rand(B, H, W, S, Fd, 2, generator=g) * torch.tensor([W + 2.0, H + 2.0]) - 1.0
+    coords[0, 0, 0, 0, 0, 0] = float("nan")
+    coords[0, 1, 1, 0, 0] = torch.tensor([3.0, 2.0])            # integral coordinate: ceil == floor
+    coords[1, 2, 2, 1, 1] = torch.tensor([W - 1.0, H - 1.0])    # last pixel
+    want = oracle.back_project(inp, coords)
+    x0, x1, y0, y1, _ = oracle.back_project_index_grids(coords, H, W)
+    out, idx = m.utils.back_project(cu(inp), cu(coords), return_index_grids=True)
+    assert torch.equal(idx.cpu(), torch.stack((x0, x1, y0, y1), dim=-1))
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=0, atol=1e-6)
+    # vectorised path (C % 4 == 0)
+    inp8 = torch.randn(B, H, W, Fd, 8, generator=g)
+    np.testing.assert_allclose(m.utils.back_project(cu(inp8), cu(coords)).cpu().numpy(),
+                               oracle.back_project(inp8, coords).numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [(2, 9, 13, 3, 16, 1), (1, 16, 16, 16, 16, 2), (2, 15, 20, 24, 40, 2), (1, 8, 12, 122, 128, 1),
+                                 (1, 6, 20, 470, 128, 1), (2, 10, 7, 16, 5, 1), (1, 33, 47, 64, 96, 2), (1, 12, 40, 238, 128, 1)])
+def test_conv3x3_vs_oracle(cfg):
+    m = _m4d()
+    b, h, w, cin, cout, stride = cfg
+    g = torch.Generator().manual_seed(cin * cout + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, stride))
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(cout, stride)
+    conv.assign(k, bias, "cuda")
+    out = conv(cu(x), alpha=0.1, algo=1).clone()
+    np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    # input living inside a wider (strided) buffer, as the refiner input does
+    xs = (cin + 3) // 4 * 4 + 4
+    wide = torch.full((b, h, w, xs), 7.0)
+    wide[..., :cin] = x
+    out2 = conv(cu(wide)[..., :cin], alpha=0.1, algo=1)
+    assert torch.equal(out2, out)
+
+
+def test_resize_and_prologue_epilogue_vs_oracle():
+    m = _m4d()
+    L = m._lib
+    g = torch.Generator().manual_seed(11)
+    b, ih, iw, h, w = 2, 8, 10, 15, 20
+    cam = camera_for("tartan", b, h, w)
+    rot, trans = motion(g, b)
+    other = torch.randn(b, ih, iw, 4, generator=g)
+    para = torch.rand(b, ih, iw, 1, generator=g) * 4 + 0.2
+    depth = torch.rand(b, ih, iw, 1, generator=g) * 40 + 1
+    state = torch.rand(b, h, w, 1, generator=g) * 40 + 3
+    want_other = oracle.resize_bilinear_legacy(other, h, w)
+    want_para = oracle.resize_bilinear_legacy(para, h, w) * 2.0
+    want_depth = oracle.resize_bilinear_legacy(depth, h, w)
+    want_pt = oracle.prev_d2para(state, rot, trans, cam)
+    e = lambda *s: torch.empty(*s, device="cuda")
+    o_pl, o_dl, o_ot, o_pt, x_in = e(b, h, w, 1), e(b, h, w, 1), e(b, h, w, 4), e(b, h, w, 1), torch.zeros(b, h, w, 12, device="cuda")
+    d = [cu(t) for t in (other, para, depth, state, rot, trans, cam["f"], cam["c"])]
+    L.check(L.lib.m4d_level_prologue(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), ih, iw, d[3].data_ptr(), d[4].data_ptr(), 4,
+                                     d[5].data_ptr(), d[6].data_ptr(), d[7].data_ptr(), b, h, w, o_pl.data_ptr(), o_dl.data_ptr(),
+                                     o_ot.data_ptr(), o_pt.data_ptr(), x_in.data_ptr(), 12, 2, 5, 0.25, L.stream()))
+    assert torch.equal(o_ot.cpu(), want_other) and torch.equal(o_pl.cpu(), want_para) and torch.equal(o_dl.cpu(), want_depth)
+    assert torch.equal(o_pt.cpu(), want_pt)
+    assert torch.equal(x_in[..., 5:9].cpu(), want_other)
+    assert torch.allclose(x_in[..., 2].cpu(), torch.log(want_para[..., 0] * 0.25), rtol=1e-6, atol=1e-6)
+    # legacy resize standalone + nearest
+    r = e(b, h, w, 4)
+    L.check(L.lib.m4d_resize_bilinear_legacy(d[0].data_ptr(), b, ih, iw, 4, h, w, 1.0, r.data_ptr(), 4, L.stream()))
+    assert torch.equal(r.cpu(), want_other)
+    n = e(b, 2 * h, 2 * w, 1)
+    L.check(L.lib.m4d_resize_nearest(d[3].data_ptr(), b, h, w, 1, 2 * h, 2 * w, n.data_ptr(), L.stream()))
+    assert torch.equal(n.cpu(), oracle.resize_nearest(state, 2 * h, 2 * w))
+    # epilogue
+    rr = torch.randn(b, h, w, 5, generator=g) * 3
+    rr[0, 0, 0, 0] = 9.0       # clipped at 7
+    o_p, o_d, o_o, o_s = e(b, h, w, 1), e(b, h, w, 1), e(b, h, w, 4), e(b, h, w, 1)
+    L.check(L.lib.m4d_level_epilogue(cu(rr).data_ptr(), 5, d[4].data_ptr(), 4, d[5].data_ptr(), d[6].data_ptr(), d[7].data_ptr(),
+                                     b, h, w, 2.0, o_p.data_ptr(), o_d.data_ptr(), o_o.data_ptr(), o_s.data_ptr(), L.stream()))
+    want_p = torch.exp(torch.clamp(rr[..., :1], -7., 7.)) / 0.5
+    assert torch.allclose(o_p.cpu(), want_p, rtol=2e-6, atol=0)
+    want_d = oracle.parallax2depth(o_p.cpu(), rot, trans, cam)
+    assert torch.equal(o_d.cpu(), want_d) and torch.equal(o_s, o_d) and torch.equal(o_o.cpu(), rr[..., 1:])
+
+
+def test_group_l2norm_and_dn_vs_oracle():
+    m = _m4d()
+    L = m._lib
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 9, 11, 96, generator=g)
+    out = torch.empty_like(x, device="cuda")
+    L.check(L.lib.m4d_group_l2norm(cu(x).data_ptr(), 2 * 9 * 11, 96, 4, out.data_ptr(), L.stream()))
+    np.testing.assert_allclose(out.cpu().numpy(), oracle.group_l2_normalize(x, 4).numpy(), rtol=5e-7, atol=0)
+    # DN at an encoder-like shape, random affine, fused leaky
+    xx = torch.randn(2, 48, 64, 16, generator=g) * (torch.rand(1, 1, 1, 16, generator=g) * 2 + 0.1) + torch.randn(1, 1, 1, 16, generator=g)
+    sc, bi = torch.rand(1, 1, 1, 16, generator=g) + 0.5, torch.randn(1, 1, 1, 16, generator=g) * 0.1
+    dn = m.DomainNormalization()
+    dn.scale, dn.bias = cu(sc), cu(bi)
+    want = oracle.leaky_relu(oracle.DomainNormalization(sc, bi)(xx))
+    np.testing.assert_allclose(dn.call(cu(xx), leaky_alpha=0.1).cpu().numpy(), want.numpy(), rtol=1e-5, atol=2e-6)
+
+
+def test_metrics_vs_oracle():
+    m = _m4d()
+    g = torch.Generator().manual_seed(17)
+    gt = torch.rand(2, 32, 48, 1, generator=g) * 100 - 5
+    est = gt * torch.exp(torch.randn(2, 32, 48, 1, generator=g) * 0.3)
+    want = oracle.depth_metrics(gt, est)
+    got = m.metrics.depth_metrics(cu(gt), cu(est)).cpu()
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=2e-5, atol=1e-7)
+
+
+# ------------------------------------------------------------------------- headline size (BASELINE config 3, L2)
+def test_pscv_headline_size_vs_oracle_and_batch_independence():
+    """96x320x32, cuts 2, r=4, b=8 (the roofline configuration): bit-exact vs the oracle on the full tensor, and the
+    batched launch equals eight single-image launches (sequences never interact)."""
+    m = _m4d()
+    b, h, w, c, cuts = 8, 96, 320, 32, 2
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(1234, b, h, w, c, cuts, "kitti")
+    dc = dev_cam(cam)
+    d = [cu(t) for t in (c1, c2, pt, pl, rot, trans)]
+    cv, pd = m.utils.get_parallax_sweeping_cv(d[0], d[1], d[2], d[3], d[4], d[5], dc, 4, nbre_cuts=cuts)
+    want_cv, want_pd = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, use_cuda_backproject=False)
+    assert torch.equal(cv.cpu(), want_cv) and torch.equal(pd.cpu(), want_pd)
+    for i in (0, 5):
+        cvi, pdi = m.utils.get_parallax_sweeping_cv(d[0][i:i + 1], d[1][i:i + 1], d[2][i:i + 1], d[3][i:i + 1], d[4][i:i + 1],
+                                                    d[5][i:i + 1], {"f": dc["f"][i:i + 1], "c": dc["c"][i:i + 1]}, 4, nbre_cuts=cuts)
+        assert torch.equal(cvi[0], cv[i]) and torch.equal(pdi[0], pd[i])
+
+
+def test_model_streaming_graph_equals_eager():
+    """6 levels, 5 frames with a trajectory reset in the middle: CUDA-graph replay is bit-identical to eager execution."""
+    m = _m4d()
+    g = torch.Generator().manual_seed(23)
+    nl, b, H, W = 6, 2, 128, 192
+    w = oracle.init_weights(nl, seed=3, bias_std=0.05, dn_random=True)
+    cam = dev_cam(camera_for("kitti", b, H, W))
+    outs = {}
+    for graph in (False, True):
+        model = m.M4Depth(nbre_levels=nl, use_cuda_graph=graph)
+        model.load_weights(w)
+        gg = torch.Generator().manual_seed(29)
+        res = []
+        for t in range(9):
+            rot, trans = motion(gg, b)
+            rgb = torch.rand(b, H, W, 3, generator=gg)
+            s = {"RGB_im": cu(rgb), "rot": cu(rot), "trans": cu(trans), "new_traj": [t in (0, 5)] * b}
+            res.append(model([[s], cam])["depth"].clone())
+        outs[graph] = res
+    for a, bb in zip(outs[False], outs[True]):
+        assert torch.equal(a, bb)
+    assert float(outs[True][0].min()) == 1000.0        # frame 0 is the new-trajectory pass-through
