@@ -16,6 +16,8 @@ the product to fp16.  ``tf.reduce_mean`` over fp16 does not have a defined summa
 """
 import torch
 
+from ._ieee import sqrt as ieee_sqrt
+
 from .geometry import _epipolar_terms
 from .warp import dense_image_warp
 
@@ -64,7 +66,7 @@ def get_parallax_sweeping_cv(c1, c2, disp_prev_t, disp, rot, trans, camera, sear
     dy = g["dy"].view(1, b, h, w, 1)
     start = torch.stack((g["sx"], g["sy"]), dim=-1).view(1, b, h, w, 2)
     proj = torch.stack((g["px"], g["py"]), dim=-1).view(1, b, h, w, 2)
-    s = torch.sqrt(dx * dx + dy * dy)                              # :261
+    s = ieee_sqrt(dx * dx + dy * dy)                              # :261
     div = s / d                                                    # :262
     delta = torch.cat((dx / div, dy / div), dim=-1)                # :263
     flow = (proj + delta) - start                                  # :264

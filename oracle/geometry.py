@@ -12,6 +12,8 @@ same order, so index grids are bit-exact between oracle and kernels.
 """
 import torch
 
+from ._ieee import sqrt as ieee_sqrt
+
 F32 = torch.float32
 
 
@@ -96,7 +98,7 @@ def _epipolar_terms(fmap, rot, trans, camera):
     stz = (t[:, 2] * 1.0).view(b, 1, 1)
     dx = stx - stz * px
     dy = sty - stz * py
-    s = torch.sqrt(dx * dx + dy * dy)
+    s = ieee_sqrt(dx * dx + dy * dy)
     sx = coords[..., 0] * fx
     sy = coords[..., 1] * fy
     return dict(alpha=alpha, px=px, py=py, dx=dx, dy=dy, s=s, sx=sx, sy=sy, stz=stz,
@@ -134,7 +136,7 @@ def prev_d2para(prev_d, rot, trans, camera):
     vx = (stx - tz * sx) / den
     vy = (sty - tz * sy) / den
     # tf.norm(axis) = sqrt(reduce_sum(x*x))
-    return torch.sqrt(vx * vx + vy * vy).unsqueeze(-1)
+    return ieee_sqrt(vx * vx + vy * vy).unsqueeze(-1)
 
 
 def pscv_query_points(disp, rot, trans, camera, search_range):

@@ -14,6 +14,8 @@ from collections import namedtuple
 import math
 
 import torch
+
+from ._ieee import sqrt as ieee_sqrt
 import torch.nn.functional as TF
 
 from .geometry import parallax2depth, prev_d2para
@@ -106,7 +108,7 @@ def group_l2_normalize(f, nbre_cuts):
     """reshape [b,h,w,cuts,-1]; x / sqrt(sum(x^2)) per group, no epsilon (m4depth_network.py:180-186)."""
     b, h, w, c = f.shape
     g = f.reshape(b, h, w, nbre_cuts, c // nbre_cuts)
-    n = torch.sqrt((g * g).sum(dim=-1, keepdim=True))
+    n = ieee_sqrt((g * g).sum(dim=-1, keepdim=True))
     return (g / n).reshape(b, h, w, c)
 
 

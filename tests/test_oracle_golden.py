@@ -105,3 +105,12 @@ def test_model_matches_reference(golden_dir, case):
             check_depth(lvl.depth_prev_t.numpy(), g[f"state_depth_{t}_l{li + 1}"], t)
         t += 1
     assert t >= 2
+
+
+def test_oracle_sqrt_is_correctly_rounded():
+    """oracle._ieee.sqrt (numpy / hardware sqrtps) equals the float64 route, which is correctly rounded for fp32."""
+    from oracle._ieee import sqrt
+    g = torch.Generator().manual_seed(0)
+    x = torch.exp(torch.rand(1 << 18, generator=g) * 40 - 20)
+    want = torch.from_numpy(np.sqrt(x.numpy().astype(np.float64)).astype(np.float32))
+    assert torch.equal(sqrt(x), want)

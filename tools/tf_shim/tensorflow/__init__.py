@@ -332,8 +332,14 @@ def _un(f):
     return lambda x, name=None: Tensor(f(convert_to_tensor(x).t))
 
 
+def _ieee_sqrt(t):
+    # torch.sqrt (MKL VML) is not correctly rounded in fp32; TF's Eigen sqrt is.  numpy's sqrt is the hardware one.
+    import numpy as _np
+    return _torch.from_numpy(_np.sqrt(t.detach().contiguous().numpy())).reshape(t.shape)
+
+
 sqrt, exp, log, floor, ceil, abs, square = (_un(f) for f in (   # noqa: A001
-    _torch.sqrt, _torch.exp, _torch.log, _torch.floor, _torch.ceil, _torch.abs, lambda t: t * t))
+    _ieee_sqrt, _torch.exp, _torch.log, _torch.floor, _torch.ceil, _torch.abs, lambda t: t * t))
 rsqrt = _un(_torch.rsqrt)
 
 
@@ -392,7 +398,7 @@ def matmul(a, b, name=None, **kw):
 
 def norm(tensor, ord='euclidean', axis=None, keepdims=None, name=None):
     t = convert_to_tensor(tensor).t
-    return Tensor(_torch.sqrt((t * t).sum(dim=_axes(axis, t.dim()), keepdim=bool(keepdims))))
+    return Tensor(_ieee_sqrt((t * t).sum(dim=_axes(axis, t.dim()), keepdim=bool(keepdims))))
 
 
 def load_op_library(path):
