@@ -61,6 +61,10 @@ struct PscvArgs {
   int cv_stride, pd_stride, cl_stride;
   float cl_scale;
   int64_t npix;
+  // 1, -1 and -0 as RUN-TIME values: ptxas folds fma(fma(a,b,-0),1,c) into fma(a,b,c) when it can see the constants,
+  // which removes a rounding the reference performs (observed in SASS; cv then differs by one fp16 ulp in ~1e-4 of
+  // the outputs).  Read from the parameter bank, they are opaque to the optimiser.
+  float one, neg_one, neg_zero;
 };
 
 enum { kGather = 0, kBP = 1, kBPFma = 2 };
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(256) pscv_kernel(PscvArgs a) {
   __syncthreads();
 
   // ---- phase 1: gather + bilinear + fp16 products, one (pixel, channel quad) per thread
-  const u64 NZ2 = pk(-0.f, -0.f), ONE2 = pk(1.f, 1.f), NEG2 = pk(-1.f, -1.f);
+  const u64 NZ2 = pk(a.neg_zero, a.neg_zero), ONE2 = pk(a.one, a.one), NEG2 = pk(a.neg_one, a.neg_one);
   const float4* __restrict__ c1v = reinterpret_cast<const float4*>(a.c1);
   const float4* __restrict__ c2v = reinterpret_cast<const float4*>(a.c2);
   for (int it = tid; it < TP * Q; it += blockDim.x) {
@@ -282,6 +286,7 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
   if (a.TP > 64) a.TP = 64;
   a.cv_stride = cv_pix_stride; a.pd_stride = pd_pix_stride; a.cl_stride = centre_log_pix_stride;
   a.cl_scale = centre_log_scale; a.npix = npix;
+  a.one = 1.0f; a.neg_one = -1.0f; a.neg_zero = -0.0f;
   const size_t smem = (size_t)a.TP * K * sizeof(TapRec) + (size_t)a.TP * a.Q * K * sizeof(float) + (size_t)a.TP * sizeof(PixRec);
   M4D_REQUIRE(smem <= 200 * 1024, "m4d_pscv_fused_fwd: c=%d needs %zu bytes of shared memory", c, smem);
   const int grid = (int)cdiv64(npix, a.TP);

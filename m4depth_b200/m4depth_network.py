@@ -189,6 +189,7 @@ class DepthEstimatorLevel:
         self.interp = L.INTERP_GATHER
         self.shape = None
         self.trace = None           # optional dict: tests set it to {} to receive clones of intermediates
+        self.pscv_events = None     # optional list: receives (start, end) CUDA events around the PSCV launch
 
     # ---- state variables, as in the reference (:160-163)
     @property
@@ -282,12 +283,18 @@ class DepthEstimatorLevel:
 
         # :220-221 fused backproject + PSCV -> cv channels and log(prev_disp centre) (:238)
         want_prev = self.ch_logprev >= 0
+        if self.pscv_events is not None:               # bench.py: CUDA events around this launch (in-situ roofline)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         L.check(L.lib.m4d_pscv_fused_fwd_ex(
             L.ptr(cur), L.ptr(prev_f_maps), L.ptr(self._para_prev_t) if want_prev else None, L.ptr(self._para_prev_l),
             L.ptr(rot), rd, L.ptr(trans), L.ptr(cam_f), L.ptr(cam_c), b, h, w, c, cuts, 4,
             self._x_in.data_ptr() + 4 * self.ch_cv, self.xs, None, 0,
             (self._x_in.data_ptr() + 4 * self.ch_logprev) if want_prev else None, self.xs, scale, None,
             self.interp, st))
+        if self.pscv_events is not None:
+            ev1.record()
+            self.pscv_events.append((ev0, ev1))
         # :232 SNCV
         if self.ch_sncv >= 0:
             L.check(L.lib.m4d_sncv_fwd(L.ptr(cur), L.ptr(cur), b, h, w, c, cuts, 3,
