@@ -60,6 +60,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 ABI_VERSION = lib.m4d_abi_version()
 
 INTERP_GATHER, INTERP_BP, INTERP_BP_FMA = 0, 1, 2
+INTERP_FLAG_GENERIC = 0x100     # OR into interp: shape-generic PSCV kernel instead of the specialised one
 
 
 class M4DError(RuntimeError):

@@ -248,6 +248,318 @@ __global__ void __launch_bounds__(256) pscv_kernel(PscvArgs a) {
   }
 }
 
+
+// =====================================================================================================================
+// Fast path: search_range 4 (K = 9, the only value the network uses, m4depth_network.py:220) and the pyramid's channel
+// counts.  Same arithmetic as the generic kernel above, restructured around what the first ncu capture showed
+// (profiles/r1a_pscv_l2_full.md: issue-bound, 82 M warp instructions, L1 hit rate 83 %):
+//   * everything that was a run-time division (K, Q, cuts*K) is a compile-time constant or a reciprocal multiply;
+//   * 2-D pixel tiles (8x8 at level 2) instead of 1-D runs: the taps of a tile overlap in both directions, so fewer
+//     c2 lines are fetched from L2 per SM;
+//   * the four taps of the gather convention are one base address plus constant / uniform offsets (x1 = x0+1, y1 = y0+1
+//     always, dense_image_warp.py:146), one 16-byte record per (pixel, k);
+//   * the k loop is fully unrolled, partial sums stay in registers; lerps are FADD2 / FFMA2 on packed f32x2 and the
+//     fp32 sum of the four fp16 products is a chain of mixed-precision FHADD (add.rn.f32.f16), 4 instead of 7 ops;
+//   * the tap loads of hypothesis k+1 are issued before the arithmetic of hypothesis k (the second capture,
+//     profiles/r1b_pscv9_l2_full.md, showed 68 % of the stall samples on the first use of the taps), and the CTA keeps its
+//     shared memory small (15 KB) so that most of the 228 KB stays L1 for the gathers.
+template <int C>
+struct FastCfg {
+  static constexpr int Q = C / 4;
+  static constexpr int NT = (Q == 24 || Q == 48) ? 144 : 128;
+  static constexpr int PPT = 1;
+  static constexpr int TP = PPT * NT / Q;                 // 32, 16, 8, 6, 4, 3 pixels per CTA
+  static constexpr int TW = TP == 32 ? 8 : TP == 16 ? 4 : TP == 8 ? 4 : TP == 6 ? 3 : TP == 4 ? 2 : 3;
+  static constexpr int TH = TP / TW;
+  static_assert(TW * TH == TP, "tile");
+};
+
+struct FastPix {
+  Epi e;
+  float para_l;
+  int x, y;          // x < 0: outside the image (partial tile)
+  uint32_t p;        // linear pixel index (b*H + y)*W + x
+};
+
+struct FastArgs {
+  PscvArgs a;
+  int tiles_x, tiles_y;
+  uint32_t WQ;       // W * Q: float4 distance between image rows
+  float inv_per_pix; // 1 / (cuts * 9)
+  float inv_gw;      // 1 / group width when it is a power of two, else 0
+};
+
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// fp32 sum, in order, of the four fp16 values of two half2 registers: ((p0 + p1) + p2) + p3, each add rounded to fp32
+__device__ __forceinline__ float sum4_h(uint32_t p01, uint32_t p23) {
+  float r;
+  asm("{\n\t.reg .b16 a, b, c, d;\n\t.reg .f32 t;\n\t"
+      "mov.b32 {a, b}, %1;\n\tmov.b32 {c, d}, %2;\n\t"
+      "cvt.f32.f16 t, a;\n\tadd.rn.f32.f16 t, b, t;\n\tadd.rn.f32.f16 t, c, t;\n\tadd.rn.f32.f16 %0, d, t;\n\t}"
+      : "=f"(r) : "r"(p01), "r"(p23));
+  return r;
+}
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// fast-path record -> the generic TapRec that sample_scalar understands
+template <int MODE, int Q>
+__device__ __forceinline__ void rec_to_tap(const uint4& ri, const float4& rw, uint32_t WQ, TapRec& t) {
+  if (MODE == kGather) {
+    const bool valid = ri.w != 0u;
+    t.i[0] = valid ? ri.x : kOutside; t.i[1] = ri.x + Q; t.i[2] = ri.x + WQ; t.i[3] = ri.x + WQ + Q;
+    t.w[0] = __uint_as_float(ri.y); t.w[1] = __uint_as_float(ri.z); t.w[2] = t.w[3] = 0.f;
+  } else {
+    const bool valid = ri.w != kOutside;
+    t.i[0] = valid ? ri.x : kOutside; t.i[1] = ri.y; t.i[2] = ri.z; t.i[3] = ri.w;
+    t.w[0] = rw.x; t.w[1] = rw.y; t.w[2] = rw.z; t.w[3] = rw.w;
+  }
+}
+
+template <int C, int MODE>
+__global__ void __launch_bounds__(FastCfg<C>::NT, 8) pscv9_kernel(FastArgs fa) {
+  typedef FastCfg<C> Cfg;
+  constexpr int K = 9, R = 4, Q = Cfg::Q, NT = Cfg::NT, TP = Cfg::TP, TW = Cfg::TW, TH = Cfg::TH, PPT = Cfg::PPT;
+  constexpr int RECW = (MODE == kGather) ? 1 : 2;            // uint4 words per (pixel, k) record
+  const PscvArgs& a = fa.a;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* recs = reinterpret_cast<uint4*>(smem_raw);                              // [TP*K*RECW]
+  float* part = reinterpret_cast<float*>(recs + TP * K * RECW);                  // [NT*PPT][K]
+  FastPix* pix = reinterpret_cast<FastPix*>(part + NT * PPT * K);                // [TP]
+
+  const int tid = threadIdx.x;
+  const int H = a.h, W = a.w;
+  const int bi = blockIdx.z;
+  const int x_base = blockIdx.x * TW, y_base = blockIdx.y * TH;
+
+  // ---- phase 0a: per-pixel epipolar terms
+  if (tid < TP) {
+    FastPix pr;
+    const int x = x_base + tid % TW, y = y_base + tid / TW;
+    if (x < W && y < H) {
+      pr.x = x; pr.y = y;
+      pr.p = (uint32_t)((bi * H + y) * W + x);
+      Pose P;
+      load_pose(a.rot, a.rot_dim, a.trans, a.cam_f, a.cam_c, bi, P);
+      pr.e = epipolar(P, x, y);
+      pr.para_l = __ldg(a.para_l + pr.p);
+    } else {
+      pr.x = -1; pr.y = 0; pr.p = 0; pr.para_l = 1.f;
+      pr.e = Epi();
+    }
+    pix[tid] = pr;
+  }
+  __syncthreads();
+
+  // ---- phase 0b: query point and taps per (pixel, hypothesis)
+  // record: word 0 = {float4 index of tap (y0,x0) for q = 0, ax | idx01, ay | idx10, valid | idx11}; BP modes add the 4 weights.
+  // Records of samples that contribute 0 (outside the image / NaN query) point at the image's first pixel so that the
+  // loads of phase 1 need no branch; .w == 0 marks them.
+  for (int it = tid; it < TP * K; it += NT) {
+    const int pl = it / K, k = it - pl * K;
+    const FastPix& pr = pix[pl];
+    const uint32_t img = (uint32_t)bi * (uint32_t)(H * W);
+    uint4 ri = (MODE == kGather) ? make_uint4(img * Q, 0u, 0u, 0u) : make_uint4(img * Q, img * Q, img * Q, kOutside);
+    float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pr.x >= 0) {
+      float rho = FADD(pr.para_l, (float)(k - R));
+      rho = (rho != rho) ? rho : fminf(fmaxf(rho, 1e-6f), 1e6f);
+      const float div = FDIV(pr.e.s, rho);
+      const float ex = FDIV(pr.e.dx, div), ey = FDIV(pr.e.dy, div);
+      const float flx = FSUB(FADD(pr.e.px, ex), pr.e.sx);
+      const float fly = FSUB(FADD(pr.e.py, ey), pr.e.sy);
+      const float qy = FADD((float)pr.y, fly), qx = FADD((float)pr.x, flx);
+      Tap bt;
+      if (MODE != kGather || a.idx_dbg) {
+        const float cqx = clip_keep_nan(qx, (float)(W - 1)), cqy = clip_keep_nan(qy, (float)(H - 1));
+        bt = make_tap(cqx, cqy, W, H);
+        if (a.idx_dbg) {
+          int4 v = bt.inside ? make_int4(bt.x0, bt.x0 + bt.dxo, bt.y0, bt.y0 + bt.dyo) : make_int4(-1, -1, -1, -1);
+          reinterpret_cast<int4*>(a.idx_dbg)[(size_t)pr.p * K + k] = v;
+        }
+      }
+      if (MODE == kGather) {
+        if (qx == qx && qy == qy) {
+          const float fx0 = fminf(fmaxf(0.f, floorf(qx)), (float)(W - 2));
+          const float fy0 = fminf(fmaxf(0.f, floorf(qy)), (float)(H - 2));
+          const float ax = fminf(fmaxf(FSUB(qx, fx0), 0.f), 1.f);
+          const float ay = fminf(fmaxf(FSUB(qy, fy0), 0.f), 1.f);
+          ri = make_uint4((img + (uint32_t)((int)fy0 * W + (int)fx0)) * (uint32_t)Q, __float_as_uint(ax), __float_as_uint(ay), 1u);
+        }
+      } else if (bt.inside) {
+        tap_weights(bt.wx, bt.wy, rw.x, rw.y, rw.z, rw.w);
+        const uint32_t base = (img + (uint32_t)(bt.y0 * W + bt.x0)) * (uint32_t)Q;
+        ri.x = base;
+        ri.y = base + (uint32_t)bt.dxo * Q;
+        ri.z = base + (uint32_t)bt.dyo * fa.WQ;
+        ri.w = ri.z + (uint32_t)bt.dxo * Q;
+      }
+      if (a.prev_disp != nullptr) {                                     // function-level API: all K warped parallaxes (:280)
+        TapRec t;
+        rec_to_tap<MODE, Q>(ri, rw, fa.WQ, t);
+        a.prev_disp[(size_t)pr.p * a.pd_stride + k] = sample_scalar<MODE>(a.para_t, t, Q);
+      }
+    }
+    if (MODE == kGather) {
+      recs[it] = ri;
+    } else {
+      recs[2 * it] = ri;
+      recs[2 * it + 1] = make_uint4(__float_as_uint(rw.x), __float_as_uint(rw.y), __float_as_uint(rw.z), __float_as_uint(rw.w));
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: one (pixel, channel quad) item per thread and pass; all 9 hypotheses unrolled
+  const u64 NZ2 = pk(a.neg_zero, a.neg_zero);
+  const float4* __restrict__ c1v = reinterpret_cast<const float4*>(a.c1);
+  const unsigned char* __restrict__ c2b = reinterpret_cast<const unsigned char*>(a.c2);
+  const uint32_t row_bytes = fa.WQ * 16u;
+#pragma unroll 1
+  for (int pp = 0; pp < PPT; ++pp) {
+    const int item = tid + pp * NT;
+    const int pl = item / Q, q = item - pl * Q;
+    if (pix[pl].x < 0) continue;
+    const float4 cc = __ldg(c1v + (size_t)pix[pl].p * Q + q);
+    // thread's 64-bit base pointer kept opaque so that each tap address is ONE IMAD.WIDE (idx * 16 + base)
+    unsigned long long c2q_;
+    asm volatile("add.u64 %0, %1, %2;" : "=l"(c2q_) : "l"(reinterpret_cast<unsigned long long>(c2b)), "l"((unsigned long long)(q * 16)));
+    const unsigned char* __restrict__ c2q = reinterpret_cast<const unsigned char*>(c2q_);
+    const uint32_t rp = (uint32_t)__cvta_generic_to_shared(recs + pl * K * RECW);
+    float* my_part = part + item * K;
+
+    uint4 iv[2];
+    float4 T[2][4];
+    // issue the record read and the four tap loads of hypothesis k into buffer k & 1
+#define M4D_LOAD_TAPS(k)                                                                                       \
+    do {                                                                                                       \
+      uint4& v_ = iv[(k) & 1];                                                                                 \
+      float4* t_ = T[(k) & 1];                                                                                 \
+      v_ = lds128(rp + (k) * RECW * 16);                                                                       \
+      if (MODE == kGather) {                                                                                   \
+        const unsigned char* p0 = c2q + (size_t)v_.x * 16u;                                                    \
+        const unsigned char* p1 = p0 + row_bytes;                                                              \
+        t_[0] = __ldg(reinterpret_cast<const float4*>(p0)); t_[1] = __ldg(reinterpret_cast<const float4*>(p0 + C * 4)); \
+        t_[2] = __ldg(reinterpret_cast<const float4*>(p1)); t_[3] = __ldg(reinterpret_cast<const float4*>(p1 + C * 4)); \
+      } else {                                                                                                 \
+        const uint32_t i11 = v_.w != kOutside ? v_.w : v_.x;                                                   \
+        t_[0] = __ldg(reinterpret_cast<const float4*>(c2q + (size_t)v_.x * 16u));                              \
+        t_[1] = __ldg(reinterpret_cast<const float4*>(c2q + (size_t)v_.y * 16u));                              \
+        t_[2] = __ldg(reinterpret_cast<const float4*>(c2q + (size_t)v_.z * 16u));                              \
+        t_[3] = __ldg(reinterpret_cast<const float4*>(c2q + (size_t)i11 * 16u));                               \
+      }                                                                                                        \
+    } while (0)
+
+    M4D_LOAD_TAPS(0);
+    const __half2 h01 = __floats2half2_rn(cc.x, cc.y), h23 = __floats2half2_rn(cc.z, cc.w);     // :276 tf.cast(c1, fp16)
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k + 1 < K) M4D_LOAD_TAPS(k + 1);
+      const uint4 v = iv[k & 1];
+      const float4 t00 = T[k & 1][0], t01 = T[k & 1][1], t10 = T[k & 1][2], t11 = T[k & 1][3];
+      const bool valid = (MODE == kGather) ? (v.w != 0u) : (v.w != kOutside);
+      const u64 a00 = pk(t00.x, t00.y), b00 = pk(t00.z, t00.w), a01 = pk(t01.x, t01.y), b01 = pk(t01.z, t01.w);
+      const u64 a10 = pk(t10.x, t10.y), b10 = pk(t10.z, t10.w), a11 = pk(t11.x, t11.y), b11 = pk(t11.z, t11.w);
+      u64 va, vb;
+      if (MODE == kGather) {
+        const float axf = __uint_as_float(v.y), ayf = __uint_as_float(v.z);
+        const u64 ax = pk(axf, axf), ay = pk(ayf, ayf);
+        // top = ax*(TR-TL)+TL ; bot = ax*(BR-BL)+BL ; out = ay*(bot-top)+top, every op rounded (dense_image_warp.py:188-190).
+        // The multiply is fma(x, y, -0) with -0 read from the parameter bank: ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+        // into FFMA2 (observed in SASS, even with -fmad=false), which would drop a rounding the reference performs.
+        const u64 topa = add2(fma2(ax, sub2(a01, a00), NZ2), a00);
+        const u64 bota = add2(fma2(ax, sub2(a11, a10), NZ2), a10);
+        va = add2(fma2(ay, sub2(bota, topa), NZ2), topa);
+        const u64 topb = add2(fma2(ax, sub2(b01, b00), NZ2), b00);
+        const u64 botb = add2(fma2(ax, sub2(b11, b10), NZ2), b10);
+        vb = add2(fma2(ay, sub2(botb, topb), NZ2), topb);
+      } else {
+        const uint4 wv = lds128(rp + (k * RECW + 1) * 16);
+        const float w0 = __uint_as_float(wv.x), w1 = __uint_as_float(wv.y), w2 = __uint_as_float(wv.z), w3 = __uint_as_float(wv.w);
+        const u64 w00 = pk(w0, w0), w01 = pk(w1, w1), w10 = pk(w2, w2), w11 = pk(w3, w3);
+        if (MODE == kBP) {
+          va = add2(add2(add2(fma2(a00, w00, NZ2), fma2(a01, w01, NZ2)), fma2(a10, w10, NZ2)), fma2(a11, w11, NZ2));
+          vb = add2(add2(add2(fma2(b00, w00, NZ2), fma2(b01, w01, NZ2)), fma2(b10, w10, NZ2)), fma2(b11, w11, NZ2));
+        } else {
+          va = fma2(a11, w11, fma2(a10, w10, fma2(a01, w01, fma2(a00, w00, NZ2))));
+          vb = fma2(b11, w11, fma2(b10, w10, fma2(b01, w01, fma2(b00, w00, NZ2))));
+        }
+      }
+      float v0, v1, v2, v3;
+      upk(va, v0, v1);
+      upk(vb, v2, v3);
+      const __half2 p01 = __hmul2(h01, __floats2half2_rn(v0, v1));      // :276 fp16 operands, fp16 product
+      const __half2 p23 = __hmul2(h23, __floats2half2_rn(v2, v3));
+      const float sk = sum4_h(h2_bits(p01), h2_bits(p23));
+      my_part[k] = valid ? sk : 0.f;
+    }
+#undef M4D_LOAD_TAPS
+  }
+  __syncthreads();
+
+  // ---- phase 2: group means -> cv, cut-major channel = cut*K + k
+  const int gq = Q / a.cuts;
+  const float gw = (float)(4 * gq);
+  const int per_pix = a.cuts * K;
+  for (int it = tid; it < TP * per_pix; it += NT) {
+    const int pl = (int)(((float)it + 0.5f) * fa.inv_per_pix);
+    const int rem = it - pl * per_pix;
+    if (pix[pl].x < 0) continue;
+    const int cut = rem / K, k = rem - cut * K;
+    const float* src = part + (pl * Q + cut * gq) * K + k;
+    float acc = src[0];
+    for (int j = 1; j < gq; ++j) acc = FADD(acc, src[j * K]);
+    const float mean = fa.inv_gw != 0.f ? FMUL(acc, fa.inv_gw) : FDIV(acc, gw);
+    a.cv[(size_t)pix[pl].p * a.cv_stride + rem] = __half2float(__float2half_rn(mean));
+  }
+  // ---- log of the centre hypothesis' warped previous parallax (m4depth_network.py:238), one thread per pixel
+  if (a.centre_log != nullptr && tid < TP && pix[tid].x >= 0) {
+    const uint4 ri = recs[(tid * K + R) * RECW];
+    float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE != kGather) {
+      const uint4 wv = recs[(tid * K + R) * RECW + 1];
+      rw = make_float4(__uint_as_float(wv.x), __uint_as_float(wv.y), __uint_as_float(wv.z), __uint_as_float(wv.w));
+    }
+    TapRec t;
+    rec_to_tap<MODE, Q>(ri, rw, fa.WQ, t);
+    const float pd = sample_scalar<MODE>(a.para_t, t, Q);
+    a.centre_log[(size_t)pix[tid].p * a.cl_stride] = logf(FMUL(pd, a.cl_scale));
+  }
+}
+
+template <int C>
+static cudaError_t launch_fast(const FastArgs& fa, int interp, cudaStream_t st) {
+  typedef FastCfg<C> Cfg;
+  const PscvArgs& a = fa.a;
+  const dim3 grid(fa.tiles_x, fa.tiles_y, a.b);
+  const size_t rec_bytes = (size_t)Cfg::TP * 9 * 16;
+  const size_t rest = (size_t)Cfg::NT * Cfg::PPT * 9 * sizeof(float) + (size_t)Cfg::TP * sizeof(FastPix);
+  cudaError_t e = cudaSuccess;
+#define M4D_PSCV9_LAUNCH(MODE, RECW)                                                                            \
+  do {                                                                                                          \
+    const size_t smem = rec_bytes * (RECW) + rest;                                                              \
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(pscv9_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) pscv9_kernel<C, MODE><<<grid, Cfg::NT, smem, st>>>(fa);                               \
+  } while (0)
+  if (interp == kGather) M4D_PSCV9_LAUNCH(kGather, 1);
+  else if (interp == kBP) M4D_PSCV9_LAUNCH(kBP, 2);
+  else M4D_PSCV9_LAUNCH(kBPFma, 2);
+#undef M4D_PSCV9_LAUNCH
+  return e;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -266,6 +578,8 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
   M4D_REQUIRE(rot_dim == 3 || rot_dim == 4, "m4d_pscv_fused_fwd: rot_dim must be 3 or 4");
   M4D_REQUIRE(search_range >= 0 && search_range <= 8, "m4d_pscv_fused_fwd: search_range must be in [0,8] (got %d)", search_range);
   M4D_REQUIRE(c % cuts == 0 && (c / cuts) % 4 == 0, "m4d_pscv_fused_fwd: group width c/cuts must be a multiple of 4 (c=%d cuts=%d)", c, cuts);
+  const bool force_generic = (interp & M4D_INTERP_FLAG_GENERIC) != 0;
+  interp &= ~M4D_INTERP_FLAG_GENERIC;
   M4D_REQUIRE(interp >= 0 && interp <= 2, "m4d_pscv_fused_fwd: bad interp mode %d", interp);
   M4D_REQUIRE(interp != kGather || (h >= 2 && w >= 2), "m4d_pscv_fused_fwd: the gather convention needs h,w >= 2");
   M4D_REQUIRE(aligned16(c1) && aligned16(c2), "m4d_pscv_fused_fwd: feature maps must be 16-byte aligned");
@@ -287,11 +601,37 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
   a.cv_stride = cv_pix_stride; a.pd_stride = pd_pix_stride; a.cl_stride = centre_log_pix_stride;
   a.cl_scale = centre_log_scale; a.npix = npix;
   a.one = 1.0f; a.neg_one = -1.0f; a.neg_zero = -0.0f;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  const bool fast_c = c == 16 || c == 32 || c == 64 || c == 96 || c == 128 || c == 192;
+  if (search_range == 4 && fast_c && b <= 65535 && !force_generic) {
+    FastArgs fa;
+    fa.a = a;
+    fa.WQ = (uint32_t)w * (uint32_t)a.Q;
+    fa.inv_per_pix = 1.0f / (float)(cuts * K);
+    const int gwi = c / cuts;
+    fa.inv_gw = (gwi & (gwi - 1)) == 0 ? 1.0f / (float)gwi : 0.f;
+#define M4D_FAST_CASE(CC)                                                \
+  case CC:                                                               \
+    fa.tiles_x = (w + FastCfg<CC>::TW - 1) / FastCfg<CC>::TW;            \
+    fa.tiles_y = (h + FastCfg<CC>::TH - 1) / FastCfg<CC>::TH;            \
+    M4D_REQUIRE(fa.tiles_y <= 65535, "m4d_pscv_fused_fwd: image too tall for the grid"); \
+    e = launch_fast<CC>(fa, interp, st);                                 \
+    break;
+    switch (c) {
+      M4D_FAST_CASE(16) M4D_FAST_CASE(32) M4D_FAST_CASE(64) M4D_FAST_CASE(96) M4D_FAST_CASE(128) M4D_FAST_CASE(192)
+    }
+#undef M4D_FAST_CASE
+    if (e != cudaSuccess) {
+      m4d_set_error("m4d_pscv_fused_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return M4D_ECUDA;
+    }
+    M4D_CHECK_LAUNCH("m4d_pscv_fused_fwd");
+    return M4D_OK;
+  }
   const size_t smem = (size_t)a.TP * K * sizeof(TapRec) + (size_t)a.TP * a.Q * K * sizeof(float) + (size_t)a.TP * sizeof(PixRec);
   M4D_REQUIRE(smem <= 200 * 1024, "m4d_pscv_fused_fwd: c=%d needs %zu bytes of shared memory", c, smem);
   const int grid = (int)cdiv64(npix, a.TP);
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaSuccess;
 #define M4D_PSCV_LAUNCH(MODE)                                                                                   \
   do {                                                                                                          \
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(pscv_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

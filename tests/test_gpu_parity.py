@@ -110,6 +110,42 @@ def test_pscv_golden(golden_dir, case, branch):
     assert np.array_equal(cv.cpu().numpy(), g["cv_" + branch])
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 80, 32, 2), (1, 15, 20, 128, 4), (2, 8, 10, 192, 8), (1, 30, 41, 96, 4),
+                                   (1, 37, 53, 16, 1), (1, 9, 33, 64, 2), (1, 12, 16, 96, 3), (1, 7, 9, 64, 1)])
+@pytest.mark.parametrize("interp", [0, 1, 2])
+def test_pscv_specialised_kernel_equals_generic_kernel(shape, interp):
+    """The K=9 specialised kernel (2-D tiles, partial tiles at the borders, every pyramid channel count, odd group
+    counts) is bit-identical to the shape-generic kernel, including prev_disp, the tap grids and the fused
+    log(centre) output the pipeline consumes."""
+    m = _m4d()
+    L = m._lib
+    b, h, w, c, cuts = shape
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(100 + h + c, b, h, w, c, cuts, "kitti")
+    pl[:, : h // 3] -= 6.0                     # negative parallax + k: clipped hypotheses; large ones leave the image
+    pl[:, -2:] *= 40.0
+    args = [cu(x) for x in (c1, c2, pt, pl, rot, trans)]
+    dc = dev_cam(cam)
+    res = []
+    for flag in (0, L.INTERP_FLAG_GENERIC):
+        cv, pd, idx = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=interp | flag, return_index_grids=True)
+        xs = cuts * 9 + 3
+        wide = torch.full((b, h, w, xs), -7.0, device="cuda")
+        L.check(L.lib.m4d_pscv_fused_fwd_ex(
+            L.ptr(args[0]), L.ptr(args[1]), L.ptr(args[2]), L.ptr(args[3]), L.ptr(args[4]), 4, L.ptr(args[5]), L.ptr(dc["f"]),
+            L.ptr(dc["c"]), b, h, w, c, cuts, 4, wide.data_ptr() + 4, xs, None, 0, wide.data_ptr() + 4 * (xs - 1), xs, 0.5,
+            None, interp | flag, L.stream()))
+        res.append((cv.cpu(), pd.cpu(), idx.cpu(), wide.cpu()))
+    for a_, b_ in zip(*res):
+        assert torch.equal(a_.view(torch.int32) if a_.dtype == torch.float32 else a_,
+                           b_.view(torch.int32) if b_.dtype == torch.float32 else b_)
+    cv, pd, _, wide = res[0]
+    assert torch.equal(wide[..., 1:1 + cuts * 9], cv) and torch.all(wide[..., 0] == -7.0) and torch.all(wide[..., cuts * 9 + 1] == -7.0)
+    want = torch.log(pd[..., 4] * 0.5)
+    got = wide[..., -1]
+    ok = torch.isfinite(want)
+    assert torch.equal(torch.isfinite(got), ok) and torch.allclose(got[ok], want[ok], rtol=2e-6, atol=2e-6)
+
+
 @pytest.mark.parametrize("case", ["l2", "l6"])
 def test_sncv_golden(golden_dir, case):
     m = _m4d()

@@ -55,10 +55,24 @@ def pscv(b=8):
         if smooth:
             pl = torch.nn.functional.avg_pool2d(pl.permute(0, 3, 1, 2), 9, 1, 4).permute(0, 2, 3, 1).contiguous()
         bytes_p9 = 4 * h * w * (2 * c + 2 + 9 * cuts + 9) * b
-        for mode, name in ((0, "gather"), (1, "bp"), (2, "bp_fma")):
-            med, mn = timeit(lambda: m.utils.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, interp=mode))
-            print(f"pscv L{lvl} {h}x{w}x{c} b={b} {name:7s}: median {med:8.1f} us  min {mn:8.1f} us  -> {bytes_p9 / mn / 1e3:7.1f} GB/s "
-                  f"({bytes_p9 / mn / 1e3 / PEAK * 100:5.1f}% of measured HBM peak, P=9 bytes {bytes_p9 / 1e6:.1f} MB)")
+        bytes_p1 = 4 * h * w * (2 * c + 2 + 9 * cuts + 1) * b
+        if os.environ.get("LEVELS") and str(lvl) not in os.environ["LEVELS"].split(","):
+            continue
+        L = m._lib
+        cv = torch.empty(b, h, w, 9 * cuts, device="cuda"); pd = torch.empty(b, h, w, 9, device="cuda"); cl = torch.empty(b, h, w, device="cuda")
+        st = L.stream()
+
+        def raw(mode, p9):
+            # direct C-ABI call on preallocated outputs: no host-side allocation between the timing events
+            L.check(L.lib.m4d_pscv_fused_fwd_ex(L.ptr(c1), L.ptr(c2), L.ptr(pt), L.ptr(pl), L.ptr(rot), 4, L.ptr(trans), L.ptr(cam["f"]),
+                                                L.ptr(cam["c"]), b, h, w, c, cuts, 4, L.ptr(cv), 9 * cuts, L.ptr(pd) if p9 else None, 9,
+                                                None if p9 else L.ptr(cl), 1, 0.5, None, mode, st))
+        for mode, name in ((0, "gather"), (1, "bp"), (2, "bp_fma"), (0x100, "gather/generic")):
+            for p9 in (True, False):
+                med, mn = timeit(lambda: raw(mode, p9))
+                nb = bytes_p9 if p9 else bytes_p1
+                print(f"pscv L{lvl} {h}x{w}x{c} b={b} {name:14s} P={9 if p9 else 1}: median {med:8.1f} us  min {mn:8.1f} us  -> {nb / med / 1e3:7.1f} GB/s "
+                      f"({nb / med / 1e3 / PEAK * 100:5.1f}% of measured HBM peak, {nb / 1e6:.1f} MB)")
 
 
 def sncv(b=8):
