@@ -129,10 +129,25 @@ int m4d_domain_norm(const float* x, int b, int h, int w, int c, const float* sca
 /* Keras Conv2D(3x3, padding='same') + bias + optional leaky_relu (:63-72,104-114; TF SAME padding rule).
  * x [b,h,w,cin] with row stride x_pix_stride (>= cin); kernel HWIO [3,3,cin,cout]; y [b,oh,ow,cout] with row
  * stride y_pix_stride, oh = ceil(h/stride).  leaky_alpha = 1 means no activation.
- * algo: 0 = auto, 1 = FFMA direct, 2 = tcgen05 3xTF32 (M4D_ENOTSUP if the shape does not fit). */
+ * algo: 0 = auto, 1 = FFMA2 direct (the only kernel that takes unpacked weights; 2 is reserved and returns M4D_ENOTSUP:
+ * the tensor-core path is m4d_conv3x3_tc_fwd below). */
 int m4d_conv3x3_nhwc(const float* x, int x_pix_stride, const float* kernel_hwio, const float* bias,
                      int b, int h, int w, int cin, int cout, int stride, float leaky_alpha,
                      float* y, int y_pix_stride, int algo, void* stream);
+
+/* Tensor-core (tcgen05, 3xTF32) path of the same stride-1 convolution, for the refiner layers that hold ~95 % of a frame's
+ * FLOPs (m4depth_network.py:104-114).  Weights are split into TF32 hi / lo planes and packed once per layer:
+ *   m4d_conv3x3_tc_packed_floats  size (in floats) of the packed buffer; 0 if (cin, cout) is outside the path
+ *                                 (cout must be a multiple of 16 in [16,128]; any cin)
+ *   m4d_conv3x3_tc_pack           kernel HWIO [3,3,cin,cout] -> packed (device buffer of that size, 16-byte aligned)
+ *   m4d_conv3x3_tc_fwd            y = leaky(conv(x) + bias); x / y pixel strides must be multiples of 4 floats and the
+ *                                 pointers 16-byte aligned, else M4D_ENOTSUP (callers fall back to m4d_conv3x3_nhwc).
+ * Result: every product is evaluated as hi*hi + hi*lo + lo*hi with fp32 accumulation, i.e. to ~2^-22 relative - the same
+ * accuracy class as the FFMA kernel, with a different summation order. */
+int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout);
+int m4d_conv3x3_tc_pack(const float* kernel_hwio, int cin, int cout, float* packed, void* stream);
+int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
+                       int cin, int cout, float leaky_alpha, float* y, int y_pix_stride, void* stream);
 
 /* tf.compat.v1.image.resize_bilinear, align_corners=False, no half-pixel (:202-204); post_scale multiplies the
  * result (parallax is doubled after resizing).  in [b,ih,iw,c] -> out [b,oh,ow,c] with row stride. */

@@ -370,6 +370,44 @@ def test_conv3x3_vs_oracle(cfg):
     assert torch.equal(out2, out)
 
 
+@pytest.mark.parametrize("cfg", [(1, 16, 8, 32, 16), (2, 16, 16, 64, 128), (1, 24, 80, 122, 128), (2, 13, 21, 128, 96),
+                                 (1, 6, 20, 470, 128), (1, 33, 47, 96, 64), (1, 12, 40, 238, 32), (1, 20, 9, 16, 16),
+                                 (1, 48, 64, 128, 128)])
+def test_conv3x3_tcgen05_3xtf32_vs_oracle(cfg):
+    """The tensor-core path (tcgen05, 3xTF32: hi*hi + hi*lo + lo*hi with fp32 accumulation) against the fp32 oracle conv
+    and against the FFMA2 kernel; partial tiles, channel counts that are not multiples of 32 (TMA zero fill), inputs
+    living inside a wider pixel stride.  Tolerance: 1e-5 of the tensor scale (north_star allows 1e-4)."""
+    m = _m4d()
+    b, h, w, cin, cout = cfg
+    g = torch.Generator().manual_seed(cin * cout + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, 1))
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(cout, 1)
+    conv.assign(k, bias, "cuda")
+    assert conv.packed is not None
+    xs = (cin + 3) // 4 * 4
+    wide = torch.full((b, h, w, xs + 4), 7.0)
+    wide[..., :cin] = x
+    xin = cu(wide)[..., :cin]
+    ffma = conv(xin, alpha=0.1, algo=1).clone()
+    tc = conv(xin, alpha=0.1, algo=2).clone()
+    scale = float(want.abs().max())
+    np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * scale)
+    np.testing.assert_allclose(tc.cpu().numpy(), ffma.cpu().numpy(), rtol=1e-5, atol=1e-5 * scale)
+    # against an fp64 evaluation: the 3xTF32 error must stay in the fp32 class (single-pass TF32 would be ~5e-4 of the
+    # scale).  The tensor core adds each K=8 partial product to the fp32 accumulator with truncation, so its error
+    # grows with the number of accumulations (9 taps x cin/8) and is a few times the FFMA kernel's.
+    ref64 = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), k.double().permute(3, 2, 0, 1), bias.double(), padding=1)
+    ref64 = torch.nn.functional.leaky_relu(ref64, 0.1).permute(0, 2, 3, 1)
+    e_tc = float((tc.cpu().double() - ref64).abs().max()) / scale
+    e_ffma = float((ffma.cpu().double() - ref64).abs().max()) / scale
+    print(f"cin={cin} cout={cout}: max error / scale  tcgen05 3xTF32 {e_tc:.2e}   FFMA2 {e_ffma:.2e}")
+    assert e_tc < 4e-6
+
+
 def test_resize_and_prologue_epilogue_vs_oracle():
     m = _m4d()
     L = m._lib

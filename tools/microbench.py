@@ -102,10 +102,16 @@ def conv(b=8):
         x = torch.randn(b, h, w, xs, device="cuda", generator=g)[..., :ci]
         cv = _Conv2D(co, s)
         cv.assign(torch.randn(3, 3, ci, co) * 0.05, torch.zeros(co), "cuda")
-        med, mn = timeit(lambda: cv(x, alpha=0.1), iters=5)
+        if os.environ.get("CONV_ONLY") and not name.startswith(tuple(os.environ["CONV_ONLY"].split(","))):
+            continue
+        algo = int(os.environ.get("CONV_ALGO", "0"))
+        if algo == 2 and cv.packed is None:
+            algo = 1
+        med, mn = timeit(lambda: cv(x, alpha=0.1, algo=algo), iters=5)
         fl = 2.0 * 9 * ci * co * (-(-h // s)) * (-(-w // s)) * b
         tot += med; totf += fl
-        print(f"conv {name:8s} {h:4d}x{w:4d} {ci:3d}->{co:3d} s{s}: {med:9.1f} us  {fl / med / 1e6:7.2f} TFLOP/s")
+        path = "tc" if (algo != 1 and cv.packed is not None and ci >= cv.tc_min_cin) else "ffma"
+        print(f"conv {name:8s} {h:4d}x{w:4d} {ci:3d}->{co:3d} s{s} {path:4s}: {med:9.1f} us  {fl / med / 1e6:7.2f} TFLOP/s")
     print(f"conv total {tot / 1e3:.2f} ms per step of {b} frames, {totf / tot / 1e6:.2f} TFLOP/s average")
 
 
