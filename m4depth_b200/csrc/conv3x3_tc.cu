@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -39,6 +40,8 @@ struct TcArgs {
   int h, w, cout, ys, kblocks;
   float alpha;
   uint32_t tmem_cols;
+  int dbg;           // timing experiments only (M4D_TC_DEBUG): 1 = reuse resident weight slabs, 2 = skip halo reload + split, 4 = no stores
+  int cs;            // thread-block cluster size along x (1 or 2): the CTAs of a cluster share every weight slab
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -72,6 +75,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
+}
+// one rank's share of a weight slab, delivered to the same shared-memory offset (and mbarrier) of every CTA in the cluster
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -152,7 +174,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     for (int s = 0; s < B_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, a.cs);          // a slot is free once EVERY CTA of the cluster has consumed it
     }
     mbar_init(acc_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,7 +184,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (a.cs > 1) cluster_sync_all();            // peers' barriers must be initialised before multicast data / commits reach them
+  else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
@@ -174,6 +197,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % A_STAGES;
         mbar_wait(a_empty + 8 * s, ((kb / A_STAGES) & 1) ^ 1);
+        if ((a.dbg & 2) && kb >= A_STAGES) { mbar_arrive(a_full + 8 * s); continue; }
         mbar_expect_tx(a_full + 8 * s, A_BYTES);
         tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
       }
@@ -182,13 +206,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      const int rank = a.cs > 1 ? (int)cluster_rank() : 0;
+      const int rows = 2 * a.cout / a.cs;                       // this CTA's share of the [hi|lo][Cout] rows
+      const uint16_t mask = (uint16_t)((1u << a.cs) - 1u);
       int it = 0;
       for (int kb = 0; kb < KB; ++kb)
         for (int tap = 0; tap < 9; ++tap, ++it) {
           const int s = it % B_STAGES;
           mbar_wait(b_empty + 8 * s, ((it / B_STAGES) & 1) ^ 1);
-          mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
-          tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, (kb * 9 + tap) * 2 * a.cout);
+          if ((a.dbg & 1) && it >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
+          mbar_expect_tx(b_full + 8 * s, b_stage_bytes);        // whole slab: own share + the peers' multicast shares
+          const uint32_t dst = sB + s * b_stage_bytes + (uint32_t)(rank * rows) * 128u;
+          const int row = (kb * 9 + tap) * 2 * a.cout + rank * rows;
+          if (a.cs > 1) tma_load_2d_mc(dst, &tmap_w, b_full + 8 * s, 0, row, mask);
+          else tma_load_2d(dst, &tmap_w, b_full + 8 * s, 0, row);
         }
     }
   } else if (warp == 2) {
@@ -227,7 +258,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             tc_mma_tf32(tmem_base + 3 * ncol, da_hi, db_lo, idesc, 1);
             started |= (1u << jm) | 8u;
           }
-          tc_commit(b_empty + 8 * sb);
+          if (a.cs > 1) tc_commit_mc(b_empty + 8 * sb, (uint16_t)((1u << a.cs) - 1u));
+          else tc_commit(b_empty + 8 * sb);
         }
         tc_commit(a_empty + 8 * sa);
       }
@@ -241,7 +273,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_wait(a_full + 8 * s, (kb / A_STAGES) & 1);
       const uint32_t hi_p = sA + s * 2 * A_SLOT, lo_p = hi_p + A_SLOT;
 #pragma unroll 4
-      for (int i = t; i < A_BYTES / 16; i += 128) {
+      for (int i = ((a.dbg & 2) && kb >= A_STAGES) ? A_BYTES : t; i < A_BYTES / 16; i += 128) {
         const uint4 v = lds128(hi_p + i * 16);
         uint4 hi, lo;
         split_tf32(v.x, hi.x, lo.x);
@@ -276,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int i = 0; i < 32; ++i)
           if (i < nc) sum[i] = j == 0 ? __uint_as_float(v[i]) : sum[i] + __uint_as_float(v[i]);
       }
-      if (valid) {
+      if (valid && !(a.dbg & 4)) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < nc) {
@@ -299,6 +331,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
+  if (a.cs > 1) cluster_sync_all();            // a peer's commit may still be in flight towards this CTA's barriers
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -376,6 +409,12 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     return M4D_ECUDA;
   }
   const int kb = tc_kblocks(cin);
+  const int tiles_x = (w + TILE_W - 1) / TILE_W;
+  static const int cs_env = [] { const char* e = getenv("M4D_TC_CS"); return e ? atoi(e) : 0; }();
+  // CTA pairs along x can share each weight slab through TMA multicast (M4D_TC_CS=2).  Measured on B200 it is ~4 % slower than
+  // independent CTAs: the kernel is bound by the tensor pipe and the per-tile prologue / epilogue, not by L2 -> SM weight traffic
+  // (profiles/r1c_conv_tc_full.md and DESIGN.md), so 1 is the default.
+  const int cs = (cs_env == 2 && tiles_x >= 2) ? 2 : 1;
   CUtensorMap mx, mw;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
@@ -392,7 +431,7 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   {
     const cuuint64_t dims[2] = {KC, (cuuint64_t)kb * 9 * 2 * cout};
     const cuuint64_t strides[1] = {KC * 4};
-    const cuuint32_t box[2] = {KC, (cuuint32_t)(2 * cout)};
+    const cuuint32_t box[2] = {KC, (cuuint32_t)(2 * cout / cs)};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -414,8 +453,29 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     }
     attr_set = true;
   }
-  const dim3 grid((w + TILE_W - 1) / TILE_W, (h + TILE_H - 1) / TILE_H, b);
-  conv3x3_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mx, mw, a);
+  a.cs = cs;
+  {
+    static const int dbg = [] { const char* e = getenv("M4D_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    a.dbg = dbg;
+    const char* e2 = getenv("M4D_TC_CS");
+    (void)e2;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((tiles_x + cs - 1) / cs * cs, (h + TILE_H - 1) / TILE_H, b);     // columns past the image compute on zero fill, store nothing
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, mx, mw, a);
+  if (le != cudaSuccess) {
+    m4d_set_error("m4d_conv3x3_tc_fwd: launch failed: %s", cudaGetErrorString(le));
+    (void)cudaGetLastError();
+    return M4D_ECUDA;
+  }
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
 }
