@@ -138,10 +138,10 @@ int m4d_conv3x3_nhwc(const float* x, int x_pix_stride, const float* kernel_hwio,
 /* Tensor-core (tcgen05, 3xTF32) path of the same stride-1 convolution, for the refiner layers that hold ~95 % of a frame's
  * FLOPs (m4depth_network.py:104-114).  Weights are split into TF32 hi / lo planes and packed once per layer:
  *   m4d_conv3x3_tc_packed_floats  size (in floats) of the packed buffer; 0 if (cin, cout) is outside the path
- *                                 (cout must be a multiple of 16 in [16,128]; any cin)
+ *                                 (1 <= cout <= 128, padded internally to a multiple of 16; any cin)
  *   m4d_conv3x3_tc_pack           kernel HWIO [3,3,cin,cout] -> packed (device buffer of that size, 16-byte aligned)
- *   m4d_conv3x3_tc_fwd            y = leaky(conv(x) + bias); x / y pixel strides must be multiples of 4 floats and the
- *                                 pointers 16-byte aligned, else M4D_ENOTSUP (callers fall back to m4d_conv3x3_nhwc).
+ *   m4d_conv3x3_tc_fwd            y = leaky(conv(x) + bias); the x pixel stride must be a multiple of 4 floats and x
+ *                                 16-byte aligned (TMA), else M4D_ENOTSUP (callers fall back to m4d_conv3x3_nhwc).
  * Result: every product is evaluated as hi*hi + hi*lo + lo*hi with fp32 accumulation, i.e. to ~2^-22 relative - the same
  * accuracy class as the FFMA kernel, with a different summation order. */
 int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout);

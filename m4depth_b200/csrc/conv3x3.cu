@@ -169,6 +169,59 @@ __global__ void __launch_bounds__(256) conv3x3_ffma_kernel(ConvArgs a) {
   }
 }
 
+// ---- thin-input layer (the RGB conv, m4depth_network.py:63 with cin = 3): one output pixel x all COUT channels per thread.
+// The FFMA2 tile kernel above wastes 5/8 of its input-channel chunk and 3/4 of its channel tile on this shape; here the
+// 27 x 16 weights sit in shared memory (broadcast reads), the 9 x cin inputs come from L1, and the layer becomes what it
+// should be: bound by the 252 MB it writes.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv3x3_thin_kernel(ConvArgs a) {
+  __shared__ __align__(16) float s_w[9 * 4 * COUT];
+  __shared__ float s_b[COUT];
+  for (int e = threadIdx.x; e < 9 * a.cin * COUT; e += 256) s_w[e] = __ldg(a.wgt + e);       // HWIO is already [tap][ci][co]
+  if (threadIdx.x < COUT) s_b[threadIdx.x] = __ldg(a.bias + threadIdx.x);
+  __syncthreads();
+  const int64_t npix = (int64_t)a.b * a.h * a.w;
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < npix; p += (int64_t)gridDim.x * 256) {
+    const int x = (int)(p % a.w), y = (int)((p / a.w) % a.h);
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int gy = y + ky - 1;
+      if (gy < 0 || gy >= a.h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int gx = x + kx - 1;
+        if (gx < 0 || gx >= a.w) continue;
+        const float* xp = a.x + (p + (int64_t)(ky - 1) * a.w + (kx - 1)) * a.xs;
+        for (int ci = 0; ci < a.cin; ++ci) {
+          const float v = __ldg(xp + ci);
+          const float4* wp = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * a.cin + ci) * COUT);
+#pragma unroll
+          for (int q = 0; q < COUT / 4; ++q) {
+            const float4 w4 = wp[q];
+            acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+    float* o = a.y + p * a.ys;
+#pragma unroll
+    for (int q = 0; q < COUT / 4; ++q) {
+      float4 v;
+      v.x = leaky(acc[4 * q + 0] + s_b[4 * q + 0], a.alpha);
+      v.y = leaky(acc[4 * q + 1] + s_b[4 * q + 1], a.alpha);
+      v.z = leaky(acc[4 * q + 2] + s_b[4 * q + 2], a.alpha);
+      v.w = leaky(acc[4 * q + 3] + s_b[4 * q + 3], a.alpha);
+      reinterpret_cast<float4*>(o)[q] = v;
+    }
+  }
+}
+
 }  // namespace
 
 // TF 'SAME' padding: out = ceil(in/s); total = max((out-1)*s + 3 - in, 0); before = total / 2
@@ -201,6 +254,14 @@ extern "C" int m4d_conv3x3_nhwc(const float* x, int x_pix_stride, const float* k
   a.b = b; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.xs = x_pix_stride; a.ys = y_pix_stride; a.alpha = leaky_alpha;
   same_pad(h, stride, a.oh, a.pad_t);
   same_pad(w, stride, a.ow, a.pad_l);
+  if (stride == 1 && cin <= 4 && cout == 16 && y_pix_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+    const int64_t npix = (int64_t)b * h * w;
+    const int64_t want = (npix + 255) / 256;
+    const int grid = (int)(want < (int64_t)m4d_sm_count() * 16 ? want : (int64_t)m4d_sm_count() * 16);
+    conv3x3_thin_kernel<16><<<grid, 256, 0, st>>>(a);
+    M4D_CHECK_LAUNCH("m4d_conv3x3_nhwc");
+    return M4D_OK;
+  }
   a.tiles_x = (a.ow + TWD - 1) / TWD;
   const int tiles_y = (a.oh + TH - 1) / TH;
   dim3 grid(a.tiles_x * tiles_y, (cout + TN - 1) / TN, b);

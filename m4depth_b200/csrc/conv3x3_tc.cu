@@ -37,9 +37,11 @@ constexpr int NTHREADS = 256;
 struct TcArgs {
   const float* bias;
   float* y;
-  int h, w, cout, ys, kblocks;
+  int h, w, cout, ys, kblocks;      // cout = MMA N = output channels rounded up to 16
+  int cout_real;                    // channels actually stored
   float alpha;
   uint32_t tmem_cols;
+  int vec_out;       // float4 stores allowed (cout_real % 4 == 0, ys % 4 == 0, y 16-byte aligned)
   int dbg;           // timing experiments only (M4D_TC_DEBUG): 1 = reuse resident weight slabs, 2 = skip halo reload + split, 4 = no stores
   int cs;            // thread-block cluster size along x (1 or 2): the CTAs of a cluster share every weight slab
 };
@@ -309,17 +311,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           if (i < nc) sum[i] = j == 0 ? __uint_as_float(v[i]) : sum[i] + __uint_as_float(v[i]);
       }
       if (valid && !(a.dbg & 4)) {
+        if (a.vec_out) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j < nc) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
-            float4 o;
-            o.x = leaky(sum[j + 0] + bv.x, a.alpha);
-            o.y = leaky(sum[j + 1] + bv.y, a.alpha);
-            o.z = leaky(sum[j + 2] + bv.z, a.alpha);
-            o.w = leaky(sum[j + 3] + bv.w, a.alpha);
-            *reinterpret_cast<float4*>(yp + c0 + j) = o;
+          for (int j = 0; j < 32; j += 4) {
+            if (j < nc && c0 + j < a.cout_real) {
+              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
+              float4 o;
+              o.x = leaky(sum[j + 0] + bv.x, a.alpha);
+              o.y = leaky(sum[j + 1] + bv.y, a.alpha);
+              o.z = leaky(sum[j + 2] + bv.z, a.alpha);
+              o.w = leaky(sum[j + 3] + bv.w, a.alpha);
+              *reinterpret_cast<float4*>(yp + c0 + j) = o;
+            }
           }
+        } else {                                                 // cout not a multiple of 4 (the 5-channel output layer)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nc && c0 + j < a.cout_real) yp[c0 + j] = leaky(sum[j] + __ldg(a.bias + c0 + j), a.alpha);
         }
       }
     }
@@ -336,7 +344,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
 // ------------------------------------------------------------------------------------------ weight packing
 // HWIO [3,3,cin,cout] -> [kb][tap][hi|lo][cout][32]: row ((kb*9+tap)*2+hl)*cout+co, column ci - 32*kb (zero beyond cin)
-__global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int cout, int kblocks, float* __restrict__ out) {
+__global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int cout_real, int cout, int kblocks, float* __restrict__ out) {
   const int64_t n = (int64_t)kblocks * 9 * cout * KC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % KC);
@@ -344,7 +352,7 @@ __global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int
     const int tap = (int)((i / ((int64_t)KC * cout)) % 9);
     const int kb = (int)(i / ((int64_t)KC * cout * 9));
     const int ci = kb * KC + c;
-    const float v = ci < cin ? w[((size_t)tap * cin + ci) * cout + co] : 0.f;
+    const float v = (ci < cin && co < cout_real) ? w[((size_t)tap * cin + ci) * cout_real + co] : 0.f;
     uint32_t hi, lo, lo_r;
     split_tf32(__float_as_uint(v), hi, lo);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_r) : "f"(__uint_as_float(lo)));
@@ -370,7 +378,8 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-inline bool tc_shape_ok(int cin, int cout) { return cin >= 1 && cout >= 16 && cout <= 128 && cout % 16 == 0; }
+inline bool tc_shape_ok(int cin, int cout) { return cin >= 1 && cout >= 1 && cout <= 128; }
+inline int tc_cout_pad(int cout) { return (cout + 15) / 16 * 16; }
 inline int tc_kblocks(int cin) { return (cin + KC - 1) / KC; }
 
 }  // namespace
@@ -379,16 +388,17 @@ extern "C" {
 
 int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout) {
   if (!tc_shape_ok(cin, cout)) return 0;
-  return (int64_t)tc_kblocks(cin) * 9 * 2 * cout * KC;
+  return (int64_t)tc_kblocks(cin) * 9 * 2 * tc_cout_pad(cout) * KC;
 }
 
 int m4d_conv3x3_tc_pack(const float* kernel_hwio, int cin, int cout, float* packed, void* stream) {
   M4D_REQUIRE(kernel_hwio && packed, "m4d_conv3x3_tc_pack: null pointer");
-  M4D_REQUIRE(tc_shape_ok(cin, cout), "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d (cout must be a multiple of 16 in [16,128])", cin, cout);
+  M4D_REQUIRE(tc_shape_ok(cin, cout), "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d (cout must be in [1,128])", cin, cout);
   const int kb = tc_kblocks(cin);
-  const int64_t n = (int64_t)kb * 9 * cout * KC;
+  const int cp = tc_cout_pad(cout);
+  const int64_t n = (int64_t)kb * 9 * cp * KC;
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, kb, packed);
+  conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, cp, kb, packed);
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
   return M4D_OK;
 }
@@ -397,9 +407,9 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
                        int cout, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
   M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
   M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
-  if (!tc_shape_ok(cin, cout) || x_pix_stride % 4 != 0 || y_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
-      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(y) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u) ||
-      (reinterpret_cast<uintptr_t>(bias) & 15u) || b > 65535 || (h + TILE_H - 1) / TILE_H > 65535) {
+  if (!tc_shape_ok(cin, cout) || x_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
+      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u) || b > 65535 ||
+      (h + TILE_H - 1) / TILE_H > 65535) {
     m4d_set_error("m4d_conv3x3_tc_fwd: shape / alignment outside the tcgen05 path (cin=%d cout=%d xs=%d ys=%d)", cin, cout, x_pix_stride, y_pix_stride);
     return M4D_ENOTSUP;
   }
@@ -409,6 +419,9 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     return M4D_ECUDA;
   }
   const int kb = tc_kblocks(cin);
+  const int cout_real = cout;
+  const bool vec_out = cout % 4 == 0 && y_pix_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15u) && !(reinterpret_cast<uintptr_t>(bias) & 15u);
+  cout = tc_cout_pad(cout);                    // from here on: the MMA N / packed row count
   const int tiles_x = (w + TILE_W - 1) / TILE_W;
   static const int cs_env = [] { const char* e = getenv("M4D_TC_CS"); return e ? atoi(e) : 0; }();
   // CTA pairs along x can share each weight slab through TMA multicast (M4D_TC_CS=2).  Measured on B200 it is ~4 % slower than
@@ -441,7 +454,8 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     }
   }
   TcArgs a;
-  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
+  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.vec_out = vec_out ? 1 : 0;
+  a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
   a.tmem_cols = cout <= 16 ? 64 : cout <= 32 ? 128 : cout <= 64 ? 256 : 512;      // 4 accumulators of cout columns, power of two
   const size_t smem = 1024 + (size_t)A_STAGES * 2 * A_SLOT + (size_t)B_STAGES * 2 * cout * 128 + 256;
   static bool attr_set = false;

@@ -3,13 +3,11 @@
 //   out[b,y,x,(dy*n+dx)*cuts + k] = leaky_0.1( mean_{j in group k} c1[b,y,x,j] * c2pad[b,y+dy-r,x+dx-r,j] ),  n = 2r+1
 //
 // The reference emits n*n*cuts separate slice -> multiply -> reduce_mean ops on NCHW transposes (about 25x the
-// algorithmic traffic); here each CTA stages ONE zero-padded (TH+2r) x (TW+2r) halo tile of ONE feature group in
-// shared memory and every thread produces n*n outputs for 4 horizontally adjacent pixels out of registers:
-// per (dy, 4-channel chunk) it issues 4 + (4+2r) LDS.128 for 4*n*4 multiply-adds (packed FFMA2, even/odd channel
-// partial sums).  Shared-memory pixel stride is gw+4 floats and every lane pair starts from a different chunk so
-// that the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups.
+// algorithmic traffic); here a CTA stages zero-padded halo tiles in shared memory, keeps the correlations in registers
+// (packed FFMA2, even/odd channel partial sums) and writes each pixel's n*n*cuts outputs as one contiguous run.
 // HBM traffic: c read once (+halo re-reads served by L2), out written once.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -28,111 +26,105 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
   return d;
 }
 
-constexpr int TW = 32;      // tile width (pixels); 8 threads x 4 pixels per row
-constexpr int PX = 4;       // pixels per thread
-
 struct SncvArgs {
   const float *c1, *c2;
   float* out;
-  int b, h, w, c, cuts, gw, out_stride, tiles_x, tiles_y, TH;
+  int b, h, w, c, cuts, gw, out_stride, tiles_x, tiles_y, TH, TW;
+  unsigned long long m_nch, m_hw, m_tw, m_oc, m_tp;    // 2^32/d + 1: exact quotients for the small indices used here
 };
 
+// i / d for i < 2^20 or so, d >= 1, with m = 2^32/d + 1 (run-time divisors, no division instruction sequence)
+__device__ __forceinline__ int fdiv(int i, unsigned long long m) { return (int)(((unsigned long long)(unsigned)i * m) >> 32); }
+
 // R = search range (compile time: the network uses 3).
+//
+// CTA = one TH x TW pixel tile, ALL feature groups; thread = (pixel, dy) with the N dx-correlations of that row of the
+// window in registers.  Per group the zero-padded (TH+2R) x (TW+2R) halo of c2 and the centre tile of c1 are staged in
+// shared memory (pixel stride gw+4 floats: the 8 lanes of a quarter warp hit 8 distinct 16-byte bank groups); per
+// 4-channel chunk a thread issues 1 + N LDS.128 and 2N FFMA2.  Results go to a shared [pixel][N*N*cuts] tile in the
+// reference's channel order (offset-major, cut-minor, :309-311) and leave as whole contiguous pixel rows: the first
+// version of this kernel wrote every value with its own 4-byte store at stride cuts (one sector per lane) and was bound
+// by that (profiles/r1a_launches.md: 182 us at level 2 for 128 MB).
 template <int R>
-__global__ void __launch_bounds__(128) sncv_kernel(SncvArgs a) {
+__global__ void __launch_bounds__(896) sncv_kernel(SncvArgs a) {
   constexpr int N = 2 * R + 1;
-  constexpr int HW_ = TW + 2 * R;          // halo tile width
   extern __shared__ __align__(16) float smem[];
   const int gw = a.gw, S = gw + 4, nch = gw / 4;
-  const int TH = a.TH, HH = TH + 2 * R;
+  const int TH = a.TH, TW = a.TW, HH = TH + 2 * R, HW_ = TW + 2 * R, TP = TH * TW;
+  const int OC = N * N * a.cuts, OS = OC | 1;          // odd pixel stride of the output tile: conflict-free column writes
   float* halo = smem;                                  // [HH][HW_][S]   (c2, zero padded)
-  float* ctr = smem + (size_t)HH * HW_ * S;            // [TH][TW][S]    (c1)
+  float* ctr = halo + (size_t)HH * HW_ * S;            // [TP][S]        (c1)
+  float* otile = ctr + (size_t)TP * S;                 // [TP][OS]
 
-  const int tile = blockIdx.x;
-  const int tx0 = (tile % a.tiles_x) * TW, ty0 = (tile / a.tiles_x) * TH;
-  const int cut = blockIdx.y, bi = blockIdx.z;
+  const int tx0 = (blockIdx.x % a.tiles_x) * TW, ty0 = (blockIdx.x / a.tiles_x) * TH;
+  const int bi = blockIdx.z;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const size_t img = (size_t)bi * a.h * a.w;
-  const int ch0 = cut * gw;
+  const int dy = fdiv(tid, a.m_tp), px = tid - dy * TP;  // blockDim = TP * N
+  const int ly = fdiv(px, a.m_tw), lx = px - ly * TW;
+  const float inv_gw = 1.0f / (float)gw;
+  const u64 Z2 = pk(0.f, 0.f);
+  const int ppr = nthr / nch;                          // pixels staged per pass
+  const int sp = fdiv(tid, a.m_nch), sj = tid - sp * nch;
 
-  // ---- stage: halo of c2 (zero outside the image = tf.pad, :293) and the centre tile of c1
-  for (int i = tid; i < HH * HW_ * nch; i += nthr) {
-    const int j = i % nch, p = i / nch;
-    const int hx = p % HW_, hy = p / HW_;
-    const int gx = tx0 + hx - R, gy = ty0 + hy - R;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gx >= 0 && gx < a.w && gy >= 0 && gy < a.h)
-      v = __ldg(reinterpret_cast<const float4*>(a.c2 + (img + (size_t)gy * a.w + gx) * a.c + ch0) + j);
-    *reinterpret_cast<float4*>(halo + (size_t)p * S + j * 4) = v;
-  }
-  for (int i = tid; i < TH * TW * nch; i += nthr) {
-    const int j = i % nch, p = i / nch;
-    const int lx = p % TW, ly = p / TW;
-    const int gx = tx0 + lx, gy = ty0 + ly;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (gx < a.w && gy < a.h)
-      v = __ldg(reinterpret_cast<const float4*>(a.c1 + (img + (size_t)gy * a.w + gx) * a.c + ch0) + j);
-    *reinterpret_cast<float4*>(ctr + (size_t)p * S + j * 4) = v;
+  for (int cut = 0; cut < a.cuts; ++cut) {
+    const int ch0 = cut * gw;
+    if (cut) __syncthreads();                          // everyone is done reading the previous group's tiles
+    // ---- stage: halo of c2 (zero outside the image = tf.pad, :293) and the centre tile of c1.
+    // nch consecutive threads per pixel (one float4 each); the (chunk, first pixel) split of tid is hoisted out of the loops
+    if (tid < ppr * nch) {
+      const float4* c2q = reinterpret_cast<const float4*>(a.c2 + ch0) + sj;
+      for (int p = sp; p < HH * HW_; p += ppr) {
+        const int hy = fdiv(p, a.m_hw), hx = p - hy * HW_;
+        const int gx = tx0 + hx - R, gy = ty0 + hy - R;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < a.w && gy >= 0 && gy < a.h) v = __ldg(c2q + (img + (size_t)gy * a.w + gx) * (a.c / 4));
+        *reinterpret_cast<float4*>(halo + (size_t)p * S + sj * 4) = v;
+      }
+      const float4* c1q = reinterpret_cast<const float4*>(a.c1 + ch0) + sj;
+      for (int p = sp; p < TP; p += ppr) {
+        const int py = fdiv(p, a.m_tw);
+        const int gx = tx0 + p - py * TW, gy = ty0 + py;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx < a.w && gy < a.h) v = __ldg(c1q + (img + (size_t)gy * a.w + gx) * (a.c / 4));
+        *reinterpret_cast<float4*>(ctr + (size_t)p * S + sj * 4) = v;
+      }
+    }
+    __syncthreads();
+
+    u64 acc[N];
+#pragma unroll
+    for (int d = 0; d < N; ++d) acc[d] = Z2;
+    const float* hrow = halo + ((size_t)(ly + dy) * HW_ + lx) * S;
+    const float* crow = ctr + (size_t)px * S;
+    for (int j = 0; j < nch; ++j) {
+      const float4 cv = *reinterpret_cast<const float4*>(crow + j * 4);
+      const u64 c_lo = pk(cv.x, cv.y), c_hi = pk(cv.z, cv.w);
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const float4 v = *reinterpret_cast<const float4*>(hrow + d * S + j * 4);
+        acc[d] = fma2(c_lo, pk(v.x, v.y), acc[d]);
+        acc[d] = fma2(c_hi, pk(v.z, v.w), acc[d]);
+      }
+    }
+    float* o = otile + (size_t)px * OS + (size_t)(dy * N) * a.cuts + cut;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      float lo, hi;
+      upk(acc[d], lo, hi);
+      o[d * a.cuts] = leaky((lo + hi) * inv_gw, 0.1f);            // tf.nn.leaky_relu(alpha=0.1) :311
+    }
   }
   __syncthreads();
-
-  const int g = tid & 7, row = tid >> 3;             // 8 threads per tile row
-  if (row >= TH) return;
-  const int lx0 = g * PX;
-  const int rot = (g >> 1) & 3;                       // chunk rotation -> conflict-free LDS.128
-  const float inv_gw = 1.0f / (float)gw;
-  const int gy = ty0 + row;
-  const bool row_ok = gy < a.h;
-  const u64 Z2 = pk(0.f, 0.f);
-
-  for (int dy = 0; dy < N; ++dy) {
-    u64 acc[PX][N];
-#pragma unroll
-    for (int i = 0; i < PX; ++i)
-#pragma unroll
-      for (int d = 0; d < N; ++d) acc[i][d] = Z2;
-    const float* hrow = halo + ((size_t)(row + dy) * HW_ + lx0) * S;
-    const float* crow = ctr + ((size_t)row * TW + lx0) * S;
-    for (int jj = 0; jj < nch; ++jj) {
-      int j = jj + rot;
-      if (j >= nch) j -= nch;
-      u64 c_lo[PX], c_hi[PX];
-#pragma unroll
-      for (int i = 0; i < PX; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(crow + i * S + j * 4);
-        c_lo[i] = pk(v.x, v.y);
-        c_hi[i] = pk(v.z, v.w);
-      }
-#pragma unroll
-      for (int col = 0; col < PX + 2 * R; ++col) {
-        const float4 v = *reinterpret_cast<const float4*>(hrow + col * S + j * 4);
-        const u64 n_lo = pk(v.x, v.y), n_hi = pk(v.z, v.w);
-#pragma unroll
-        for (int i = 0; i < PX; ++i) {
-          const int d = col - i;               // dx index of pixel i for this neighbour column
-          if (d >= 0 && d < N) {
-            acc[i][d] = fma2(c_lo[i], n_lo, acc[i][d]);
-            acc[i][d] = fma2(c_hi[i], n_hi, acc[i][d]);
-          }
-        }
-      }
-    }
-    if (row_ok) {
-#pragma unroll
-      for (int i = 0; i < PX; ++i) {
-        const int gx = tx0 + lx0 + i;
-        if (gx < a.w) {
-          float* o = a.out + (img + (size_t)gy * a.w + gx) * a.out_stride + (size_t)(dy * N) * a.cuts + cut;
-#pragma unroll
-          for (int d = 0; d < N; ++d) {
-            float lo, hi;
-            upk(acc[i][d], lo, hi);
-            const float m = (lo + hi) * inv_gw;
-            o[(size_t)d * a.cuts] = leaky(m, 0.1f);          // tf.nn.leaky_relu(alpha=0.1) :311
-          }
-        }
-      }
-    }
+  // ---- contiguous pixel rows out: one warp per pixel, lanes along the channels
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;      // full warps only (blockDim = 7 * TP >= 112)
+  for (int p = warp < nwarps ? warp : TP; p < TP; p += nwarps) {
+    const int py = fdiv(p, a.m_tw);
+    const int gx = tx0 + p - py * TW, gy = ty0 + py;
+    if (gx >= a.w || gy >= a.h) continue;
+    float* dst = a.out + (img + (size_t)gy * a.w + gx) * a.out_stride;
+    const float* src = otile + (size_t)p * OS;
+    for (int ch = lane; ch < OC; ch += 32) dst[ch] = src[ch];
   }
 }
 
@@ -153,14 +145,22 @@ extern "C" int m4d_sncv_fwd(const float* c1, const float* c2, int b, int h, int 
   SncvArgs a;
   a.c1 = c1; a.c2 = c2; a.out = out; a.b = b; a.h = h; a.w = w; a.c = c; a.cuts = cuts; a.gw = c / cuts;
   a.out_stride = out_pix_stride;
-  a.TH = 16;
-  const int S = a.gw + 4;
-  auto smem_for = [&](int th) { return (size_t)((th + 2 * search_range) * (TW + 2 * search_range) + th * TW) * S * sizeof(float); };
-  while (a.TH > 4 && (smem_for(a.TH) > 100 * 1024 || a.TH / 2 >= h)) a.TH /= 2;
-  const size_t smem = smem_for(a.TH);
-  M4D_REQUIRE(smem <= 200 * 1024, "m4d_sncv_fwd: group width %d needs %zu bytes of shared memory", a.gw, smem);
-  a.tiles_x = (w + TW - 1) / TW;
+  // small tiles (32 / 16 pixels, 7 threads per pixel): several independent CTAs per SM hide each other's staging latency
+  if (cuts <= 2) { a.TH = 4; a.TW = 8; }
+  else if (cuts <= 4) { a.TH = 4; a.TW = 8; }
+  else { a.TH = 4; a.TW = 4; }
+  {
+    static const char* e = getenv("M4D_SNCV_TILE");          // tuning experiments: "TH,TW"
+    int th, tw;
+    if (e && sscanf(e, "%d,%d", &th, &tw) == 2 && th * tw * n <= 896 && ((size_t)th * tw * ((n * n * cuts) | 1)) * 4 < 150 * 1024) { a.TH = th; a.TW = tw; }
+  }
+  const int S = a.gw + 4, TP = a.TH * a.TW, OS = (n * n * cuts) | 1;
+  const size_t smem = ((size_t)(a.TH + 2 * search_range) * (a.TW + 2 * search_range) * S + (size_t)TP * S + (size_t)TP * OS) * sizeof(float);
+  M4D_REQUIRE(smem <= 200 * 1024, "m4d_sncv_fwd: c=%d cuts=%d needs %zu bytes of shared memory", c, cuts, smem);
+  a.tiles_x = (w + a.TW - 1) / a.TW;
   a.tiles_y = (h + a.TH - 1) / a.TH;
+  auto magic = [](int d) { return (0x100000000ull / (unsigned long long)d) + 1ull; };
+  a.m_nch = magic(a.gw / 4); a.m_hw = magic(a.TW + 2 * search_range); a.m_tw = magic(a.TW); a.m_oc = magic(n * n * cuts); a.m_tp = magic(TP);
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
@@ -171,8 +171,8 @@ extern "C" int m4d_sncv_fwd(const float* c1, const float* c2, int b, int h, int 
     }
     attr_set = true;
   }
-  dim3 grid(a.tiles_x * a.tiles_y, cuts, b);
-  sncv_kernel<3><<<grid, a.TH * 8, smem, st>>>(a);
+  dim3 grid(a.tiles_x * a.tiles_y, 1, b);
+  sncv_kernel<3><<<grid, TP * n, smem, st>>>(a);
   M4D_CHECK_LAUNCH("m4d_sncv_fwd");
   return M4D_OK;
 }

@@ -73,7 +73,7 @@ class _Conv2D:
             raise L.M4DError(f"conv kernel must be [3,3,cin,{self.filters}], got {tuple(k.shape)}")
         self.kernel = k
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
-        # tensor-core path (stride-1 layers with cout a multiple of 16 <= 128): TF32 hi/lo planes packed once per layer
+        # tensor-core path (stride-1 layers with cout <= 128): TF32 hi/lo planes packed once per layer
         self.packed = None
         n = L.lib.m4d_conv3x3_tc_packed_floats(k.shape[2], self.filters) if self.strides == 1 else 0
         if n > 0:
@@ -98,12 +98,12 @@ class _Conv2D:
                 out = self._out[key] = torch.empty(self.out_shape(x), dtype=torch.float32, device=x.device)
         xs, ys = _pix_stride(x), _pix_stride(out)
         # algo: 0 = auto (tcgen05 3xTF32 where the layer was packed and the strides allow, else FFMA2), 1 = FFMA2, 2 = tcgen05
-        if algo != 1 and self.packed is not None and xs % 4 == 0 and ys % 4 == 0 and cin >= self.tc_min_cin:
+        if algo != 1 and self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin:
             L.check(L.lib.m4d_conv3x3_tc_fwd(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
                                              float(alpha), L.ptr(out), ys, L.stream()))
             return out
         if algo == 2:
-            raise L.M4DError("conv layer is outside the tcgen05 path (stride 1, cout % 16 == 0, cout <= 128, strides % 4 == 0)")
+            raise L.M4DError("conv layer is outside the tcgen05 path (stride 1, cout <= 128, cin >= 16, input pixel stride % 4 == 0)")
         L.check(L.lib.m4d_conv3x3_nhwc(L.ptr(x), xs, L.ptr(self.kernel), L.ptr(self.bias), b, h, w, cin,
                                        self.filters, self.strides, float(alpha), L.ptr(out), ys, 1, L.stream()))
         return out

@@ -372,7 +372,7 @@ def test_conv3x3_vs_oracle(cfg):
 
 @pytest.mark.parametrize("cfg", [(1, 16, 8, 32, 16), (2, 16, 16, 64, 128), (1, 24, 80, 122, 128), (2, 13, 21, 128, 96),
                                  (1, 6, 20, 470, 128), (1, 33, 47, 96, 64), (1, 12, 40, 238, 32), (1, 20, 9, 16, 16),
-                                 (1, 48, 64, 128, 128)])
+                                 (1, 48, 64, 128, 128), (2, 19, 23, 16, 5), (1, 16, 8, 40, 20)])
 def test_conv3x3_tcgen05_3xtf32_vs_oracle(cfg):
     """The tensor-core path (tcgen05, 3xTF32: hi*hi + hi*lo + lo*hi with fp32 accumulation) against the fp32 oracle conv
     and against the FFMA2 kernel; partial tiles, channel counts that are not multiples of 32 (TMA zero fill), inputs
