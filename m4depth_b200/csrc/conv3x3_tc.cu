@@ -15,9 +15,8 @@
 //     is one halo row = 1280 B.  Four "splitter" warps turn the landed fp32 halo into its hi / lo planes in place;
 //   * B: weights are pre-split and pre-packed once per layer (m4d_conv3x3_tc_pack) as K-major [k-block][tap][hi|lo][Cout][32]
 //     so that one 2-D TMA load per (k-block, tap) brings both planes;
-//   * warp roles: 0 = A producer, 1 = B producer, 2 = MMA issuer (one thread), 3 = TMEM allocator, 4-7 = splitter, then
-//     epilogue (tcgen05.ld -> bias + leaky_relu -> NHWC stores).  mbarrier pipelines: A full/ready/empty (2 stages),
-//     B full/empty (4 stages), accumulator full.
+//   * persistent, warp-specialised CTA (one per SM): see the kernel's header comment; mbarrier rings for the halo (2 stages),
+//     the weight slabs (3-6 stages) and two TMEM accumulator sets, epilogue through swizzled staging tiles and TMA stores.
 #include "common.cuh"
 
 #include <cuda.h>
@@ -31,19 +30,20 @@ constexpr int KC = 32;                                         // channels per k
 constexpr int A_BYTES = HALO_W * HALO_H * KC * 4;              // 23040: one halo plane as landed by TMA
 constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;         // 23552
 constexpr int A_STAGES = 2;
-constexpr int B_STAGES = 4;
-constexpr int NTHREADS = 256;
+constexpr int MAX_B_STAGES = 6;
+constexpr int OUT_SLOT = 128 * 128;                            // one [128 px][32 ch] fp32 staging tile
+constexpr int NTHREADS = 384;
 
 struct TcArgs {
   const float* bias;
   float* y;
   int h, w, cout, ys, kblocks;      // cout = MMA N = output channels rounded up to 16
   int cout_real;                    // channels actually stored
+  int tiles_x, tiles_y, ntiles;
+  int nb;                           // weight-slab stages that fit in shared memory (3 at Cout = 128 ... 6)
+  int nacc, nsets;                  // TMEM accumulators per tile (2 or 4) and accumulator sets (2 = epilogue overlaps the next tile)
+  int tma_out;                      // epilogue through TMA stores (ys % 4 == 0 and y 16-byte aligned), else scalar stores
   float alpha;
-  uint32_t tmem_cols;
-  int vec_out;       // float4 stores allowed (cout_real % 4 == 0, ys % 4 == 0, y 16-byte aligned)
-  int dbg;           // timing experiments only (M4D_TC_DEBUG): 1 = reuse resident weight slabs, 2 = skip halo reload + split, 4 = no stores
-  int cs;            // thread-block cluster size along x (1 or 2): the CTAs of a cluster share every weight slab
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -78,24 +78,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1)
                : "memory");
 }
-// one rank's share of a weight slab, delivered to the same shared-memory offset (and mbarrier) of every CTA in the cluster
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+// one lane of a converged warp (cute::elect_one_sync): the same lane every time, so its tcgen05.commit covers its MMAs
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -151,22 +142,34 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 }
 
 // ------------------------------------------------------------------------------------------------- the kernel
+// Persistent: one CTA per SM walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (384 threads):
+//   0      A producer   one TMA halo load per k-block                            ring of 2 halo stages
+//   1      B producer   one TMA weight-slab load per (k-block, tap)              ring of nb weight stages
+//   2      MMA issuer   warp-convergent, one elected lane issues tcgen05.mma     TMEM accumulator set j % nsets
+//   3      TMEM allocator
+//   4-7    splitter     fp32 halo -> TF32 hi (in place) + lo plane
+//   8-11   epilogue     TMEM -> registers -> bias + leaky_relu -> swizzled staging tile -> TMA store
+// All rings run across tile boundaries, so the loads and the split of tile i+1 and the whole epilogue of tile i overlap
+// with the MMAs (measured before this structure: 30 % of a 128-column tile was un-overlapped prologue + epilogue,
+// profiles/r1f_conv_tc_tile_phases.md).
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, TcArgs a) {
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const __grid_constant__ CUtensorMap tmap_y, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t b_stage_bytes = 2u * (uint32_t)a.cout * 128u;                // hi + lo planes of [Cout][32]
   const uint32_t sA = smem0;                                                  // [A_STAGES][hi, lo][A_SLOT]
-  const uint32_t sB = sA + A_STAGES * 2 * A_SLOT;                             // [B_STAGES][b_stage_bytes]
-  const uint32_t sBar = sB + B_STAGES * b_stage_bytes;
+  const uint32_t sOut = sA + A_STAGES * 2 * A_SLOT;                           // [2][128 px][32 ch] staging for the TMA stores
+  const uint32_t sB = sOut + 2 * OUT_SLOT;                                    // [nb][b_stage_bytes]
+  const uint32_t sBar = sB + (uint32_t)a.nb * b_stage_bytes;
   const uint32_t a_full = sBar, a_ready = sBar + 8 * A_STAGES, a_empty = sBar + 16 * A_STAGES;
-  const uint32_t b_full = sBar + 24 * A_STAGES, b_empty = b_full + 8 * B_STAGES;
-  const uint32_t acc_full = b_empty + 8 * B_STAGES;
-  const uint32_t tmem_slot = acc_full + 8;
+  const uint32_t b_full = sBar + 24 * A_STAGES, b_empty = b_full + 8 * MAX_B_STAGES;
+  const uint32_t acc_full = b_empty + 8 * MAX_B_STAGES, acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ox0 = blockIdx.x * TILE_W, oy0 = blockIdx.y * TILE_H, bi = blockIdx.z;
-  const int KB = a.kblocks;
+  const int KB = a.kblocks, NB = a.nb, NSETS = a.nsets;
+  const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < A_STAGES; ++s) {
@@ -174,172 +177,214 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(a_ready + 8 * s, 128);
       mbar_init(a_empty + 8 * s, 1);
     }
-    for (int s = 0; s < B_STAGES; ++s) {
+    for (int s = 0; s < MAX_B_STAGES; ++s) {
       mbar_init(b_full + 8 * s, 1);
-      mbar_init(b_empty + 8 * s, a.cs);          // a slot is free once EVERY CTA of the cluster has consumed it
+      mbar_init(b_empty + 8 * s, 1);
     }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 4);          // one elected lane of each epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 3) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  if (a.cs > 1) cluster_sync_all();            // peers' barriers must be initialised before multicast data / commits reach them
-  else __syncthreads();
+  __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // Roles 0-2 run warp-convergent (every lane walks the loops and the barrier waits) and one elected lane issues the
+  // asynchronous instructions: inside an `if (lane == 0)` region ptxas cannot keep the descriptors in uniform registers and
+  // wraps every UTCHMMA / UTMALDG in an ELECT + BRA.U.ANY loop with ~10 uniform-datapath instructions each.
   if (warp == 0) {
-    // ===== A producer: one halo load per k-block
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % A_STAGES;
-        mbar_wait(a_empty + 8 * s, ((kb / A_STAGES) & 1) ^ 1);
-        if ((a.dbg & 2) && kb >= A_STAGES) { mbar_arrive(a_full + 8 * s); continue; }
-        mbar_expect_tx(a_full + 8 * s, A_BYTES);
-        tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
+    // ===== A producer
+    if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    int ka = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
+      const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
+      for (int kb = 0; kb < KB; ++kb, ++ka) {
+        const int s = ka % A_STAGES;
+        mbar_wait(a_empty + 8 * s, ((ka / A_STAGES) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(a_full + 8 * s, A_BYTES);
+          tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-      const int rank = a.cs > 1 ? (int)cluster_rank() : 0;
-      const int rows = 2 * a.cout / a.cs;                       // this CTA's share of the [hi|lo][Cout] rows
-      const uint16_t mask = (uint16_t)((1u << a.cs) - 1u);
-      int it = 0;
-      for (int kb = 0; kb < KB; ++kb)
-        for (int tap = 0; tap < 9; ++tap, ++it) {
-          const int s = it % B_STAGES;
-          mbar_wait(b_empty + 8 * s, ((it / B_STAGES) & 1) ^ 1);
-          if ((a.dbg & 1) && it >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
-          mbar_expect_tx(b_full + 8 * s, b_stage_bytes);        // whole slab: own share + the peers' multicast shares
-          const uint32_t dst = sB + s * b_stage_bytes + (uint32_t)(rank * rows) * 128u;
-          const int row = (kb * 9 + tap) * 2 * a.cout + rank * rows;
-          if (a.cs > 1) tma_load_2d_mc(dst, &tmap_w, b_full + 8 * s, 0, row, mask);
-          else tma_load_2d(dst, &tmap_w, b_full + 8 * s, 0, row);
+    if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+      for (int kt = 0; kt < KB * 9; ++kt, ++it) {
+        const int s = it % NB;
+        mbar_wait(b_empty + 8 * s, ((it / NB) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
+          tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, kt * 2 * a.cout);
         }
-    }
+        __syncwarp();
+      }
   } else if (warp == 2) {
     // ===== MMA issuer
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lo_off = (uint32_t)a.cout * 128u;
-      // Four accumulators of Cout columns each.  The tensor core adds every K=8 partial product to the fp32 accumulator
-      // with truncation, so the error grows with the number of additions made at full magnitude: the hi*hi products
-      // are therefore spread over three accumulators (by tap column) and the two small cross terms, whose truncation
-      // errors are 2^-11 smaller, go to a fourth; the epilogue adds the four in fp32.
-      const uint32_t ncol = (uint32_t)a.cout;
-      int it = 0;
-      uint32_t started = 0;                                      // bit j: accumulator j has been written
-      for (int kb = 0; kb < KB; ++kb) {
-        const int sa = kb % A_STAGES;
-        mbar_wait(a_ready + 8 * sa, (kb / A_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = sA + sa * 2 * A_SLOT, a_lo = a_hi + A_SLOT;
-        for (int tap = 0; tap < 9; ++tap, ++it) {
-          const int sb = it % B_STAGES;
-          mbar_wait(b_full + 8 * sb, (it / B_STAGES) & 1);
-          tc_fence_after();
-          const uint32_t tap_off = (uint32_t)((tap / 3) * HALO_W + (tap % 3)) * 128u;
-          const uint32_t b_hi = sB + sb * b_stage_bytes;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t lo_off16 = ((uint32_t)a.cout * 128u) >> 4;
+    // Accumulators of Cout columns each.  The tensor core adds every K=8 partial product to the fp32 accumulator with
+    // truncation, so the error grows with the number of additions made at full magnitude: the hi*hi products are spread
+    // over nmain accumulators (by tap column) and the two small cross terms, whose truncation errors are 2^-11 smaller,
+    // go to their own; the epilogue adds them in fp32.  nmain = 3 where 2 sets x 4 x Cout columns fit in TMEM (Cout <= 64)
+    // or the layer is deep (cin > 128: one set, no epilogue overlap - only the small pyramid levels), else 1.
+    const uint32_t ncol = (uint32_t)a.cout;
+    const uint32_t nmain = (uint32_t)a.nacc - 1u;
+    int ka = 0, it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
+      const int set = j % NSETS;
+      mbar_wait(acc_empty + 8 * set, ((j / NSETS) & 1) ^ 1);            // epilogue has drained this set
+      tc_fence_after();
+      const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
+      const uint32_t d_corr = d_set + nmain * ncol;
+      for (int kb = 0; kb < KB; ++kb, ++ka) {
+        const int sa = ka % A_STAGES;
+        mbar_wait(a_ready + 8 * sa, (ka / A_STAGES) & 1);
+        // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
+        const uint64_t dA_hi = umma_desc(sA + sa * 2 * A_SLOT, HALO_W * 128);
+        const uint64_t dA_lo = umma_desc(sA + sa * 2 * A_SLOT + A_SLOT, HALO_W * 128);
+#pragma unroll 1
+        for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-          for (int ks = 0; ks < KC / 8; ++ks) {
-            const uint64_t da_hi = umma_desc(a_hi + tap_off + ks * 32, HALO_W * 128);
-            const uint64_t da_lo = umma_desc(a_lo + tap_off + ks * 32, HALO_W * 128);
-            const uint64_t db_hi = umma_desc(b_hi + ks * 32, 1024);
-            const uint64_t db_lo = umma_desc(b_hi + lo_off + ks * 32, 1024);
-            const uint32_t jm = (uint32_t)(tap % 3);
-            tc_mma_tf32(tmem_base + jm * ncol, da_hi, db_hi, idesc, (started >> jm) & 1u);
-            tc_mma_tf32(tmem_base + 3 * ncol, da_lo, db_hi, idesc, (started >> 3) & 1u);
-            tc_mma_tf32(tmem_base + 3 * ncol, da_hi, db_lo, idesc, 1);
-            started |= (1u << jm) | 8u;
+          for (int kx = 0; kx < 3; ++kx, ++it) {
+            const int sb = it % NB;
+            mbar_wait(b_full + 8 * sb, (it / NB) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t dB_hi = umma_desc(sB + sb * b_stage_bytes, 1024);
+              const uint32_t tap16 = (uint32_t)((ky * HALO_W + kx) * 128) >> 4;
+              const uint32_t jm = nmain == 3u ? (uint32_t)kx : 0u;
+              const uint32_t d_main = d_set + jm * ncol;
+              const uint32_t later = (kb > 0 || ky > 0) ? 1u : 0u;         // past the first tap row of the tile
+              const uint32_t main_started = (nmain == 3u || kx == 0) ? later : 1u;
+#pragma unroll
+              for (int ks = 0; ks < KC / 8; ++ks) {
+                const uint64_t a_hi = dA_hi + tap16 + ks * 2, a_lo = dA_lo + tap16 + ks * 2;
+                const uint64_t b_hi = dB_hi + ks * 2, b_lo = dB_hi + lo_off16 + ks * 2;
+                tc_mma_tf32(d_main, a_hi, b_hi, idesc, ks > 0 ? 1u : main_started);
+                tc_mma_tf32(d_corr, a_lo, b_hi, idesc, (ks > 0 || kx > 0) ? 1u : later);
+                tc_mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+              }
+              tc_commit(b_empty + 8 * sb);
+              if (ky == 2 && kx == 2) {
+                tc_commit(a_empty + 8 * sa);
+                if (kb == KB - 1) tc_commit(acc_full + 8 * set);
+              }
+            }
+            __syncwarp();
           }
-          if (a.cs > 1) tc_commit_mc(b_empty + 8 * sb, (uint16_t)((1u << a.cs) - 1u));
-          else tc_commit(b_empty + 8 * sb);
         }
-        tc_commit(a_empty + 8 * sa);
       }
-      tc_commit(acc_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 8) {
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes
     const int t = threadIdx.x - 128;
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % A_STAGES;
-      mbar_wait(a_full + 8 * s, (kb / A_STAGES) & 1);
-      const uint32_t hi_p = sA + s * 2 * A_SLOT, lo_p = hi_p + A_SLOT;
+    int ka = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+      for (int kb = 0; kb < KB; ++kb, ++ka) {
+        const int s = ka % A_STAGES;
+        mbar_wait(a_full + 8 * s, (ka / A_STAGES) & 1);
+        const uint32_t hi_p = sA + s * 2 * A_SLOT, lo_p = hi_p + A_SLOT;
 #pragma unroll 4
-      for (int i = ((a.dbg & 2) && kb >= A_STAGES) ? A_BYTES : t; i < A_BYTES / 16; i += 128) {
-        const uint4 v = lds128(hi_p + i * 16);
-        uint4 hi, lo;
-        split_tf32(v.x, hi.x, lo.x);
-        split_tf32(v.y, hi.y, lo.y);
-        split_tf32(v.z, hi.z, lo.z);
-        split_tf32(v.w, hi.w, lo.w);
-        sts128(hi_p + i * 16, hi);
-        sts128(lo_p + i * 16, lo);
+        for (int i = t; i < A_BYTES / 16; i += 128) {
+          const uint4 v = lds128(hi_p + i * 16);
+          uint4 hi, lo;
+          split_tf32(v.x, hi.x, lo.x);
+          split_tf32(v.y, hi.y, lo.y);
+          split_tf32(v.z, hi.z, lo.z);
+          split_tf32(v.w, hi.w, lo.w);
+          sts128(hi_p + i * 16, hi);
+          sts128(lo_p + i * 16, lo);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(a_ready + 8 * s);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(a_ready + 8 * s);
-    }
+  } else if (warp >= 8) {
     // ===== epilogue: accumulator rows (pixels) of this warp's TMEM lane quadrant
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int q = warp - 4;
+    const int q = warp - 8;
     const int m = q * 32 + lane;
-    const int oy = oy0 + m / TILE_W, ox = ox0 + m % TILE_W;
-    const bool valid = oy < a.h && ox < a.w;
-    float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < a.cout; c0 += 32) {
-      uint32_t v[32];
-      float sum[32];
-      const int nc = a.cout - c0 >= 32 ? 32 : 16;
+    const int et = threadIdx.x - 256;                              // 0..127 within the epilogue group
+    int j = 0, oc = 0;                                             // tile counter, staging-buffer use counter
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
+      const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
+      const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
+      const int set = j % NSETS;
+      mbar_wait(acc_full + 8 * set, (j / NSETS) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
+      const int oy = oy0 + m / TILE_W, ox = ox0 + m % TILE_W;
+      const bool valid = oy < a.h && ox < a.w;
+      float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
+      for (int c0 = 0; c0 < a.cout; c0 += 32, ++oc) {
+        uint32_t v[32];
+        float sum[32];
+        const int nc = a.cout - c0 >= 32 ? 32 : 16;
+        for (int jj = 0; jj < a.nacc; ++jj) {                       // (main0 [+ main1 + main2]) + cross terms
+          if (nc == 32) tc_ld32(trow + jj * a.cout + c0, v);
+          else tc_ld16(trow + jj * a.cout + c0, v);
+          tc_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {                              // ((main0 + main1) + main2) + cross terms
-        if (nc == 32) tc_ld32(trow + j * a.cout + c0, v);
-        else tc_ld16(trow + j * a.cout + c0, v);
-        tc_ld_wait();
+          for (int i = 0; i < 32; ++i)
+            if (i < nc) sum[i] = jj == 0 ? __uint_as_float(v[i]) : sum[i] + __uint_as_float(v[i]);
+        }
+        if (c0 + 32 >= a.cout) {                                    // last read of this accumulator set: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + 8 * set);
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nc) sum[i] = j == 0 ? __uint_as_float(v[i]) : sum[i] + __uint_as_float(v[i]);
-      }
-      if (valid && !(a.dbg & 4)) {
-        if (a.vec_out) {
+          if (i < nc) sum[i] = leaky(sum[i] + (c0 + i < a.cout_real ? __ldg(a.bias + c0 + i) : 0.f), a.alpha);
+        if (a.tma_out) {
+          // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
+          // row m lives at chunk c ^ (m & 7).  Two buffers; the issuing thread waits until the store that last used this
+          // buffer has finished READING it before the group overwrites it.
+          const uint32_t sbuf = sOut + (uint32_t)(oc & 1) * OUT_SLOT;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (j < nc && c0 + j < a.cout_real) {
-              const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
-              float4 o;
-              o.x = leaky(sum[j + 0] + bv.x, a.alpha);
-              o.y = leaky(sum[j + 1] + bv.y, a.alpha);
-              o.z = leaky(sum[j + 2] + bv.z, a.alpha);
-              o.w = leaky(sum[j + 3] + bv.w, a.alpha);
-              *reinterpret_cast<float4*>(yp + c0 + j) = o;
-            }
+          for (int c = 0; c < 8; ++c)
+            if (c * 4 < nc)
+              sts128(rowp + (uint32_t)((c ^ (m & 7)) * 16),
+                     make_uint4(__float_as_uint(sum[4 * c]), __float_as_uint(sum[4 * c + 1]), __float_as_uint(sum[4 * c + 2]), __float_as_uint(sum[4 * c + 3])));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_y), "r"(sbuf),
+                         "r"(c0), "r"(ox0), "r"(oy0), "r"(bi)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-        } else {                                                 // cout not a multiple of 4 (the 5-channel output layer)
+        } else if (valid) {                                         // pixel stride not a multiple of 16 bytes (the 5-channel output layer)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nc && c0 + j < a.cout_real) yp[c0 + j] = leaky(sum[j] + __ldg(a.bias + c0 + j), a.alpha);
+          for (int i = 0; i < 32; ++i)
+            if (i < nc && c0 + i < a.cout_real) yp[c0 + i] = sum[i];
         }
       }
     }
+    if (a.tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store's reads
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 3) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
-  if (a.cs > 1) cluster_sync_all();            // a peer's commit may still be in flight towards this CTA's barriers
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
@@ -408,8 +453,7 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
   M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
   if (!tc_shape_ok(cin, cout) || x_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
-      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u) || b > 65535 ||
-      (h + TILE_H - 1) / TILE_H > 65535) {
+      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u)) {
     m4d_set_error("m4d_conv3x3_tc_fwd: shape / alignment outside the tcgen05 path (cin=%d cout=%d xs=%d ys=%d)", cin, cout, x_pix_stride, y_pix_stride);
     return M4D_ENOTSUP;
   }
@@ -420,15 +464,9 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   }
   const int kb = tc_kblocks(cin);
   const int cout_real = cout;
-  const bool vec_out = cout % 4 == 0 && y_pix_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15u) && !(reinterpret_cast<uintptr_t>(bias) & 15u);
+  const bool tma_out = y_pix_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15u);
   cout = tc_cout_pad(cout);                    // from here on: the MMA N / packed row count
-  const int tiles_x = (w + TILE_W - 1) / TILE_W;
-  static const int cs_env = [] { const char* e = getenv("M4D_TC_CS"); return e ? atoi(e) : 0; }();
-  // CTA pairs along x can share each weight slab through TMA multicast (M4D_TC_CS=2).  Measured on B200 it is ~4 % slower than
-  // independent CTAs: the kernel is bound by the tensor pipe and the per-tile prologue / epilogue, not by L2 -> SM weight traffic
-  // (profiles/r1c_conv_tc_full.md and DESIGN.md), so 1 is the default.
-  const int cs = (cs_env == 2 && tiles_x >= 2) ? 2 : 1;
-  CUtensorMap mx, mw;
+  CUtensorMap mx, mw, my;
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
     const cuuint64_t strides[3] = {(cuuint64_t)x_pix_stride * 4, (cuuint64_t)w * x_pix_stride * 4, (cuuint64_t)h * w * x_pix_stride * 4};
@@ -444,7 +482,7 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   {
     const cuuint64_t dims[2] = {KC, (cuuint64_t)kb * 9 * 2 * cout};
     const cuuint64_t strides[1] = {KC * 4};
-    const cuuint32_t box[2] = {KC, (cuuint32_t)(2 * cout / cs)};
+    const cuuint32_t box[2] = {KC, (cuuint32_t)(2 * cout)};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -453,11 +491,41 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
       return M4D_ECUDA;
     }
   }
+  if (tma_out) {
+    const cuuint64_t dims[4] = {(cuuint64_t)cout_real, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
+    const cuuint64_t strides[3] = {(cuuint64_t)y_pix_stride * 4, (cuuint64_t)w * y_pix_stride * 4, (cuuint64_t)h * w * y_pix_stride * 4};
+    const cuuint32_t box[4] = {32, TILE_W, TILE_H, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled(y) failed with %d", (int)r);
+      return M4D_ECUDA;
+    }
+  } else {
+    my = mx;                                   // unused by the kernel
+  }
   TcArgs a;
-  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.vec_out = vec_out ? 1 : 0;
+  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
-  a.tmem_cols = cout <= 16 ? 64 : cout <= 32 ? 128 : cout <= 64 ? 256 : 512;      // 4 accumulators of cout columns, power of two
-  const size_t smem = 1024 + (size_t)A_STAGES * 2 * A_SLOT + (size_t)B_STAGES * 2 * cout * 128 + 256;
+  a.tiles_x = (w + TILE_W - 1) / TILE_W;
+  a.tiles_y = (h + TILE_H - 1) / TILE_H;
+  const int64_t ntiles = (int64_t)a.tiles_x * a.tiles_y * b;
+  M4D_REQUIRE(ntiles < (1ll << 30), "m4d_conv3x3_tc_fwd: too many tiles");
+  a.ntiles = (int)ntiles;
+  // TMEM: 512 columns = 2 sets of 256.  4 accumulators per tile (3 for hi*hi + 1 for the cross terms) where two sets fit
+  // (Cout <= 64) or the layer is deep (cin > 128: single set, the epilogue does not overlap - small pyramid levels only);
+  // otherwise 2 accumulators and two sets.
+  if (cout <= 64) { a.nacc = 4; a.nsets = 2; }
+  else if (kb > 4) { a.nacc = 4; a.nsets = 1; }
+  else { a.nacc = 2; a.nsets = 2; }
+  const size_t fixed = 1024 + (size_t)A_STAGES * 2 * A_SLOT + 2 * OUT_SLOT + 512;
+  const size_t stage = (size_t)2 * cout * 128;
+  int nb = (int)((227 * 1024 - fixed) / stage);
+  if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
+  M4D_REQUIRE(nb >= 2, "m4d_conv3x3_tc_fwd: not enough shared memory for the weight pipeline");
+  a.nb = nb;
+  const size_t smem = fixed + (size_t)nb * stage;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -467,29 +535,8 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     }
     attr_set = true;
   }
-  a.cs = cs;
-  {
-    static const int dbg = [] { const char* e = getenv("M4D_TC_DEBUG"); return e ? atoi(e) : 0; }();
-    a.dbg = dbg;
-    const char* e2 = getenv("M4D_TC_CS");
-    (void)e2;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((tiles_x + cs - 1) / cs * cs, (h + TILE_H - 1) / TILE_H, b);     // columns past the image compute on zero fill, store nothing
-  cfg.blockDim = dim3(NTHREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel, mx, mw, a);
-  if (le != cudaSuccess) {
-    m4d_set_error("m4d_conv3x3_tc_fwd: launch failed: %s", cudaGetErrorString(le));
-    (void)cudaGetLastError();
-    return M4D_ECUDA;
-  }
+  const int grid = a.ntiles < m4d_sm_count() ? a.ntiles : m4d_sm_count();
+  conv3x3_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mx, mw, my, a);
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
 }
