@@ -32,7 +32,7 @@ constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;         // 23552
 constexpr int A_STAGES = 2;
 constexpr int MAX_B_STAGES = 6;
 constexpr int OUT_SLOT = 128 * 128;                            // one [128 px][32 ch] fp32 staging tile
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 512;
 
 struct TcArgs {
   const float* bias;
@@ -142,13 +142,13 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 }
 
 // ------------------------------------------------------------------------------------------------- the kernel
-// Persistent: one CTA per SM walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (384 threads):
+// Persistent: one CTA per SM walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Warp roles (512 threads):
 //   0      A producer   one TMA halo load per k-block                            ring of 2 halo stages
 //   1      B producer   one TMA weight-slab load per (k-block, tap)              ring of nb weight stages
-//   2      MMA issuer   warp-convergent, one elected lane issues tcgen05.mma     TMEM accumulator set j % nsets
+//   2      MMA issuer   warp-convergent, one elected lane issues tcgen05.mma     TMEM accumulator sets alternate per k-block
 //   3      TMEM allocator
 //   4-7    splitter     fp32 halo -> TF32 hi (in place) + lo plane
-//   8-11   epilogue     TMEM -> registers -> bias + leaky_relu -> swizzled staging tile -> TMA store
+//   8-15   epilogue     per k-block: TMEM -> register sums; per tile: bias + leaky_relu -> swizzled staging tile -> TMA store
 // All rings run across tile boundaries, so the loads and the split of tile i+1 and the whole epilogue of tile i overlap
 // with the MMAs (measured before this structure: 30 % of a 128-column tile was un-overlapped prologue + epilogue,
 // profiles/r1f_conv_tc_tile_phases.md).
@@ -183,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 4);          // one elected lane of each epilogue warp
+      mbar_init(acc_empty + 8 * s, 8);          // one lane of each of the 8 epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -236,21 +236,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t lo_off16 = ((uint32_t)a.cout * 128u) >> 4;
-    // Accumulators of Cout columns each.  The tensor core adds every K=8 partial product to the fp32 accumulator with
-    // truncation, so the error grows with the number of additions made at full magnitude: the hi*hi products are spread
-    // over nmain accumulators (by tap column) and the two small cross terms, whose truncation errors are 2^-11 smaller,
-    // go to their own; the epilogue adds them in fp32.  nmain = 3 where 2 sets x 4 x Cout columns fit in TMEM (Cout <= 64)
-    // or the layer is deep (cin > 128: one set, no epilogue overlap - only the small pyramid levels), else 1.
+    // The tensor core adds every K=8 partial product to the fp32 accumulator with TRUNCATION, so the error is biased and
+    // grows with the number of additions made at full magnitude (one accumulator per tile: 1e-5 of the scale at cin = 128,
+    // and the bias survives into the depth maps).  Three measures keep the kernel in the FFMA class: every k-block starts
+    // fresh accumulators that the epilogue warps add in registers (round to nearest); the two small cross terms, whose
+    // truncation errors are 2^-11 smaller, have their own accumulator; and where TMEM has room (Cout <= 64) the hi*hi
+    // products are spread over three accumulators by tap column.
     const uint32_t ncol = (uint32_t)a.cout;
     const uint32_t nmain = (uint32_t)a.nacc - 1u;
-    int ka = 0, it = 0, j = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
-      const int set = j % NSETS;
-      mbar_wait(acc_empty + 8 * set, ((j / NSETS) & 1) ^ 1);            // epilogue has drained this set
-      tc_fence_after();
-      const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
-      const uint32_t d_corr = d_set + nmain * ncol;
+    int ka = 0, it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++ka) {
+        // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
+        const int set = ka & 1;
+        mbar_wait(acc_empty + 8 * set, ((ka >> 1) & 1) ^ 1);            // epilogue has drained this set
+        const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
+        const uint32_t d_corr = d_set + nmain * ncol;
         const int sa = ka % A_STAGES;
         mbar_wait(a_ready + 8 * sa, (ka / A_STAGES) & 1);
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
@@ -268,7 +269,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               const uint32_t tap16 = (uint32_t)((ky * HALO_W + kx) * 128) >> 4;
               const uint32_t jm = nmain == 3u ? (uint32_t)kx : 0u;
               const uint32_t d_main = d_set + jm * ncol;
-              const uint32_t later = (kb > 0 || ky > 0) ? 1u : 0u;         // past the first tap row of the tile
+              const uint32_t later = ky > 0 ? 1u : 0u;                     // past the first tap row of the k-block
               const uint32_t main_started = (nmain == 3u || kx == 0) ? later : 1u;
 #pragma unroll
               for (int ks = 0; ks < KC / 8; ++ks) {
@@ -281,7 +282,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               tc_commit(b_empty + 8 * sb);
               if (ky == 2 && kx == 2) {
                 tc_commit(a_empty + 8 * sa);
-                if (kb == KB - 1) tc_commit(acc_full + 8 * set);
+                tc_commit(acc_full + 8 * set);
               }
             }
             __syncwarp();
@@ -313,56 +314,70 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_arrive(a_ready + 8 * s);
       }
   } else if (warp >= 8) {
-    // ===== epilogue: accumulator rows (pixels) of this warp's TMEM lane quadrant
-    const int q = warp - 8;
+    // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant, group g the
+    // 32-column chunks g and g+2.  After every k-block the group adds that k-block's accumulators into its register sums and
+    // hands the set back; after the last one it applies bias + leaky_relu and stores through its staging tile.
+    const int grp = (warp - 8) >> 2, q = warp & 3;
     const int m = q * 32 + lane;
-    const int et = threadIdx.x - 256;                              // 0..127 within the epilogue group
-    int j = 0, oc = 0;                                             // tile counter, staging-buffer use counter
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
+    const int et = threadIdx.x - 256 - grp * 128;                  // 0..127 within the group
+    const uint32_t sbuf = sOut + (uint32_t)grp * OUT_SLOT;
+    const int nchunks = (a.cout + 31) >> 5;
+    int ka = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
-      const int set = j % NSETS;
-      mbar_wait(acc_full + 8 * set, (j / NSETS) & 1);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
+      float sum[2][32];
+      for (int kb = 0; kb < KB; ++kb, ++ka) {
+        const int set = ka & 1;
+        mbar_wait(acc_full + 8 * set, (ka >> 1) & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c0 = (grp + 2 * ci) * 32;
+          if (c0 < a.cout) {
+            const int nc = a.cout - c0 >= 32 ? 32 : 16;
+            for (int jj = 0; jj < a.nacc; ++jj) {                   // (main0 [+ main1 + main2]) + cross terms
+              uint32_t v[32];
+              if (nc == 32) tc_ld32(trow + jj * a.cout + c0, v);
+              else tc_ld16(trow + jj * a.cout + c0, v);
+              tc_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nc) sum[ci][i] = (kb == 0 && jj == 0) ? __uint_as_float(v[i]) : sum[ci][i] + __uint_as_float(v[i]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + 8 * set);            // all 8 epilogue warps arrive, with or without chunks
+      }
       const int oy = oy0 + m / TILE_W, ox = ox0 + m % TILE_W;
       const bool valid = oy < a.h && ox < a.w;
       float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
-      for (int c0 = 0; c0 < a.cout; c0 += 32, ++oc) {
-        uint32_t v[32];
-        float sum[32];
-        const int nc = a.cout - c0 >= 32 ? 32 : 16;
-        for (int jj = 0; jj < a.nacc; ++jj) {                       // (main0 [+ main1 + main2]) + cross terms
-          if (nc == 32) tc_ld32(trow + jj * a.cout + c0, v);
-          else tc_ld16(trow + jj * a.cout + c0, v);
-          tc_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < nc) sum[i] = jj == 0 ? __uint_as_float(v[i]) : sum[i] + __uint_as_float(v[i]);
-        }
-        if (c0 + 32 >= a.cout) {                                    // last read of this accumulator set: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + 8 * set);
-        }
+      for (int ci = 0; ci < 2; ++ci) {
+        const int c0 = (grp + 2 * ci) * 32;
+        if (grp + 2 * ci >= nchunks) continue;
+        const int nc = a.cout - c0 >= 32 ? 32 : 16;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nc) sum[i] = leaky(sum[i] + (c0 + i < a.cout_real ? __ldg(a.bias + c0 + i) : 0.f), a.alpha);
+          if (i < nc) sum[ci][i] = leaky(sum[ci][i] + (c0 + i < a.cout_real ? __ldg(a.bias + c0 + i) : 0.f), a.alpha);
         if (a.tma_out) {
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
-          // row m lives at chunk c ^ (m & 7).  Two buffers; the issuing thread waits until the store that last used this
-          // buffer has finished READING it before the group overwrites it.
-          const uint32_t sbuf = sOut + (uint32_t)(oc & 1) * OUT_SLOT;
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
+          // store has finished READING it.
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
             if (c * 4 < nc)
               sts128(rowp + (uint32_t)((c ^ (m & 7)) * 16),
-                     make_uint4(__float_as_uint(sum[4 * c]), __float_as_uint(sum[4 * c + 1]), __float_as_uint(sum[4 * c + 2]), __float_as_uint(sum[4 * c + 3])));
+                     make_uint4(__float_as_uint(sum[ci][4 * c]), __float_as_uint(sum[ci][4 * c + 1]), __float_as_uint(sum[ci][4 * c + 2]),
+                                __float_as_uint(sum[ci][4 * c + 3])));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (et == 0) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_y), "r"(sbuf),
                          "r"(c0), "r"(ox0), "r"(oy0), "r"(bi)
@@ -372,7 +387,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         } else if (valid) {                                         // pixel stride not a multiple of 16 bytes (the 5-channel output layer)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nc && c0 + i < a.cout_real) yp[c0 + i] = sum[i];
+            if (i < nc && c0 + i < a.cout_real) yp[c0 + i] = sum[ci][i];
         }
       }
     }
@@ -513,12 +528,10 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   const int64_t ntiles = (int64_t)a.tiles_x * a.tiles_y * b;
   M4D_REQUIRE(ntiles < (1ll << 30), "m4d_conv3x3_tc_fwd: too many tiles");
   a.ntiles = (int)ntiles;
-  // TMEM: 512 columns = 2 sets of 256.  4 accumulators per tile (3 for hi*hi + 1 for the cross terms) where two sets fit
-  // (Cout <= 64) or the layer is deep (cin > 128: single set, the epilogue does not overlap - small pyramid levels only);
-  // otherwise 2 accumulators and two sets.
-  if (cout <= 64) { a.nacc = 4; a.nsets = 2; }
-  else if (kb > 4) { a.nacc = 4; a.nsets = 1; }
-  else { a.nacc = 2; a.nsets = 2; }
+  // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block.  A set holds 4 accumulators (3 for hi*hi
+  // by tap column + 1 for the cross terms) where they fit (Cout <= 64), else 2.
+  a.nacc = cout <= 64 ? 4 : 2;
+  a.nsets = 2;
   const size_t fixed = 1024 + (size_t)A_STAGES * 2 * A_SLOT + 2 * OUT_SLOT + 512;
   const size_t stage = (size_t)2 * cout * 128;
   int nb = (int)((227 * 1024 - fixed) / stage);

@@ -20,9 +20,14 @@ Differences a maintainer must know:
 """
 from collections import namedtuple
 
+import os
+
 import torch
 
 from . import _lib as L
+
+# conv kernel choice for layers called with algo=0: 0 = auto (tcgen05 where packed), 1 = FFMA2 everywhere (tools/model_error.py)
+DEFAULT_CONV_ALGO = int(os.environ.get("M4D_CONV_ALGO", "0"))
 
 # m4depth_network.py:21-22
 M4depthAblationParameters = namedtuple(
@@ -97,6 +102,7 @@ class _Conv2D:
             if out is None:
                 out = self._out[key] = torch.empty(self.out_shape(x), dtype=torch.float32, device=x.device)
         xs, ys = _pix_stride(x), _pix_stride(out)
+        algo = algo or DEFAULT_CONV_ALGO
         # algo: 0 = auto (tcgen05 3xTF32 where the layer was packed and the strides allow, else FFMA2), 1 = FFMA2, 2 = tcgen05
         if algo != 1 and self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin:
             L.check(L.lib.m4d_conv3x3_tc_fwd(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
