@@ -39,6 +39,7 @@ struct TcArgs {
   float* y;
   int h, w, cout, ys, kblocks;      // cout = MMA N = output channels rounded up to 16
   int cout_real;                    // channels actually stored
+  int cin;                          // real input channels: k-steps of the last k-block that are all zero fill are skipped
   int tiles_x, tiles_y, ntiles;
   int nb;                           // weight-slab stages that fit in shared memory (3 at Cout = 128 ... 6)
   int nacc, nsets;                  // TMEM accumulators per tile (2 or 4) and accumulator sets (2 = epilogue overlaps the next tile)
@@ -257,6 +258,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
         const uint64_t dA_hi = umma_desc(sA + sa * 2 * A_SLOT, HALO_W * 128);
         const uint64_t dA_lo = umma_desc(sA + sa * 2 * A_SLOT + A_SLOT, HALO_W * 128);
+        const int rem = a.cin - kb * KC;
+        const int nks = rem >= KC ? KC / 8 : (rem + 7) >> 3;               // 16-channel inputs: 2 of the 4 k-steps are zero fill
 #pragma unroll 1
         for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
@@ -273,6 +276,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               const uint32_t main_started = (nmain == 3u || kx == 0) ? later : 1u;
 #pragma unroll
               for (int ks = 0; ks < KC / 8; ++ks) {
+                if (ks >= nks) break;
                 const uint64_t a_hi = dA_hi + tap16 + ks * 2, a_lo = dA_lo + tap16 + ks * 2;
                 const uint64_t b_hi = dB_hi + ks * 2, b_lo = dB_hi + lo_off16 + ks * 2;
                 tc_mma_tf32(d_main, a_hi, b_hi, idesc, ks > 0 ? 1u : main_started);
@@ -521,7 +525,7 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     my = mx;                                   // unused by the kernel
   }
   TcArgs a;
-  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
+  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.cin = cin; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
   a.tiles_x = (w + TILE_W - 1) / TILE_W;
   a.tiles_y = (h + TILE_H - 1) / TILE_H;

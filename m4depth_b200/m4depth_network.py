@@ -69,6 +69,7 @@ class _Conv2D:
         self.kernel = None          # [3,3,cin,cout] HWIO
         self.packed = None          # TF32 hi/lo planes for the tcgen05 path (m4d_conv3x3_tc_pack)
         self.tc_min_cin = 16        # thinner inputs (the RGB conv) stay on the FFMA2 kernel
+        self.events = None          # optional list: receives (start, end) CUDA events around the launch (bench.py roofline)
         self.bias = None            # [cout]
         self._out = {}
 
@@ -105,8 +106,14 @@ class _Conv2D:
         algo = algo or DEFAULT_CONV_ALGO
         # algo: 0 = auto (tcgen05 3xTF32 where the layer was packed and the strides allow, else FFMA2), 1 = FFMA2, 2 = tcgen05
         if algo != 1 and self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin:
+            if self.events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             L.check(L.lib.m4d_conv3x3_tc_fwd(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
                                              float(alpha), L.ptr(out), ys, L.stream()))
+            if self.events is not None:
+                ev1.record()
+                self.events.append((ev0, ev1))
             return out
         if algo == 2:
             raise L.M4DError("conv layer is outside the tcgen05 path (stride 1, cout <= 128, cin >= 16, input pixel stride % 4 == 0)")
@@ -398,6 +405,7 @@ class M4Depth:
         self._seen = set()
         self._static = None
         self._out = None
+        self._h2d = None            # side-stream upload state for host (CPU) frames
 
     # ------------------------------------------------------------------------------------------ weights
     def weight_layers(self):
@@ -471,7 +479,27 @@ class M4Depth:
             self._graphs.clear()
             self._seen.clear()
         st = self._static
-        st["RGB_im"].copy_(rgb, non_blocking=True)
+        if rgb.device.type == "cpu":
+            # Host frame: upload on a side stream into one of two staging buffers so that the copy of frame t+1 overlaps the
+            # graph of frame t (the host runs ahead of the device), then a device-to-device copy into the graph's static input.
+            if self._h2d is None or tuple(self._h2d["buf"][0].shape) != tuple(rgb.shape):
+                self._h2d = {"stream": torch.cuda.Stream(device=self.device), "idx": 0,
+                             "buf": [torch.empty_like(st["RGB_im"]) for _ in range(2)],
+                             "up": [torch.cuda.Event() for _ in range(2)], "used": [torch.cuda.Event() for _ in range(2)]}
+                for e in self._h2d["used"]:
+                    e.record()
+            hd = self._h2d
+            i = hd["idx"] = 1 - hd["idx"]
+            main = torch.cuda.current_stream()
+            hd["stream"].wait_event(hd["used"][i])          # the graph input copy that last read this staging buffer
+            with torch.cuda.stream(hd["stream"]):
+                hd["buf"][i].copy_(rgb, non_blocking=True)
+                hd["up"][i].record()
+            main.wait_event(hd["up"][i])
+            st["RGB_im"].copy_(hd["buf"][i], non_blocking=True)
+            hd["used"][i].record()
+        else:
+            st["RGB_im"].copy_(rgb, non_blocking=True)
         st["rot"].copy_(s['rot'], non_blocking=True)
         st["trans"].copy_(s['trans'], non_blocking=True)
         st["f"].copy_(camera["f"], non_blocking=True)
