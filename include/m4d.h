@@ -104,6 +104,10 @@ int m4d_pscv_fused_fwd(const float* c1, const float* c2, const float* para_prev_
 /* OR-ed into interp: use the shape-generic kernel even where the specialised one (search_range 4, c in
  * {16,32,64,96,128,192}) applies.  Same results bit for bit; tests cross-check the two implementations with it. */
 #define M4D_INTERP_FLAG_GENERIC 0x100
+/* OR-ed into interp: use the CTA-tile kernel (pscv9_kernel) where the warp-autonomous one (pscv9w_kernel; the network's
+ * (c, cuts) pairs) would run.  Same results bit for bit.  Bits 12-15, when non-zero, override the resident CTAs per SM
+ * of the persistent grid (tuning experiments only). */
+#define M4D_INTERP_FLAG_TILE 0x200
 int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
                           const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
                           int b, int h, int w, int c, int cuts, int search_range,

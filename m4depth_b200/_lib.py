@@ -64,6 +64,7 @@ ABI_VERSION = lib.m4d_abi_version()
 
 INTERP_GATHER, INTERP_BP, INTERP_BP_FMA = 0, 1, 2
 INTERP_FLAG_GENERIC = 0x100     # OR into interp: shape-generic PSCV kernel instead of the specialised one
+INTERP_FLAG_TILE = 0x200        # OR into interp: CTA-tile K=9 kernel instead of the warp-autonomous one
 
 
 class M4DError(RuntimeError):

@@ -560,6 +560,274 @@ static cudaError_t launch_fast(const FastArgs& fa, int interp, cudaStream_t st) 
   return e;
 }
 
+// =====================================================================================================================
+// Warp-autonomous kernel: same arithmetic, no CTA-wide barriers.  What the captures of pscv9_kernel showed
+// (profiles/r1b_pscv9_l2_full.md): 37 % of the warp instructions were geometry executed by mostly-empty warps (16 of
+// 128 threads active in phase 0a, a half-empty second pass in 0b), 18 % the group means with run-time index math, and
+// 26 % of the stall samples sat on the three __syncthreads.  Here one WARP owns an 8x4-pixel tile end to end:
+//   phase 0   lane = pixel: epipolar terms, then the 9 query points / tap records (all lanes busy), records -> the warp's
+//             own shared-memory slice; centre_log / prev_disp / idx_dbg written from here
+//   phase 1   lane = (pixel, channel quad) items, Q passes of 32 items; per hypothesis one broadcast LDS.128 of the
+//             record, four LDG.E.128 taps (a pass reads whole pixel rows: 128 B per quarter warp at c = 32), the un-fused
+//             lerps in packed f32x2, fp16 products, FHADD sum; taps are prefetched TWO hypotheses ahead through three
+//             register buffers (9 = 3 x 3, so the rotation is static across passes)
+//   phase 2   every PH pixels: ordered group sums from the warp's partial-sum slice, mean, fp16 round, coalesced stores
+// Only __syncwarp() separates the phases.  The grid is persistent (a multiple of the SM count); a CTA walks 16x8-pixel
+// super tiles (its four warps take the four 8x4 quadrants) so that concurrently gathered c2 rows share L1 lines.
+template <int C>
+struct WCfg {
+  static constexpr int Q = C / 4;
+  static constexpr int PH = Q <= 4 ? 32 : Q == 8 ? 16 : Q == 16 ? 8 : Q == 24 ? 4 : Q == 32 ? 4 : 2;   // pixels per phase-2 round
+  static constexpr int ROUND_PASSES = PH * Q / 32;
+  static_assert(PH * Q % 32 == 0 && 32 % PH == 0, "round");
+  static constexpr int part_bytes = ROUND_PASSES * 32 * 9 * 4;
+  __host__ __device__ static constexpr int warp_bytes(int recw) { return 32 * 9 * 16 * recw + part_bytes; }
+};
+
+struct WArgs {
+  PscvArgs a;
+  int tiles_x, tiles_y;   // 8x4-pixel warp tiles
+  int sup_x, sup_y;       // super tiles (2x2 warp tiles) per image
+  int n_sup;              // sup_x * sup_y * b
+  uint32_t WQ;
+};
+
+template <int C, int CUTS, int MODE>
+__global__ void __launch_bounds__(128, 3) pscv9w_kernel(WArgs wa) {
+  typedef WCfg<C> Cfg;
+  constexpr int K = 9, R = 4, Q = Cfg::Q, GQ = Q / CUTS, PH = Cfg::PH, RP = Cfg::ROUND_PASSES;
+  constexpr int RECW = (MODE == kGather) ? 1 : 2;
+  constexpr int REC_BYTES = 32 * K * 16 * RECW;
+  static_assert(Q % CUTS == 0, "groups");
+  const PscvArgs& a = wa.a;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + warp * Cfg::warp_bytes(RECW);
+  uint4* recs = reinterpret_cast<uint4*>(wbase);                      // [32 pixels][K][RECW]
+  float* part = reinterpret_cast<float*>(wbase + REC_BYTES);          // [RP * 32 items][K]
+  const uint32_t recs_s = (uint32_t)__cvta_generic_to_shared(recs);
+  const int H = a.h, W = a.w;
+  const u64 NZ2 = pk(a.neg_zero, a.neg_zero);
+  const float4* __restrict__ c1v = reinterpret_cast<const float4*>(a.c1);
+  const unsigned char* __restrict__ c2b = reinterpret_cast<const unsigned char*>(a.c2);
+  const uint32_t row_bytes = wa.WQ * 16u;
+  const int sup_per_img = wa.sup_x * wa.sup_y;
+
+#pragma unroll 1
+  for (int sup = blockIdx.x; sup < wa.n_sup; sup += gridDim.x) {
+    const int bi = sup / sup_per_img;
+    const int r0 = sup - bi * sup_per_img;
+    const int sy = r0 / wa.sup_x, sx = r0 - sy * wa.sup_x;
+    const int tx = sx * 2 + (warp & 1), ty = sy * 2 + (warp >> 1);
+    if (tx >= wa.tiles_x || ty >= wa.tiles_y) continue;              // warp-uniform
+    const int x_base = tx * 8, y_base = ty * 4;
+    const uint32_t img = (uint32_t)bi * (uint32_t)(H * W);
+
+    // ---- phase 0: lane = pixel (depth_operations.py:229-265, dense_image_warp.py:135-149 / 238-253)
+    {
+      const int x = x_base + (lane & 7), y = y_base + (lane >> 3);
+      const bool inimg = x < W && y < H;
+      const uint32_t p = img + (uint32_t)(y * W + x);
+      Pose P;
+      load_pose(a.rot, a.rot_dim, a.trans, a.cam_f, a.cam_c, bi, P);
+      const Epi e = epipolar(P, x, y);
+      const float para_l = inimg ? __ldg(a.para_l + p) : 1.f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        uint4 ri = (MODE == kGather) ? make_uint4(img * Q, 0u, 0u, 0u) : make_uint4(img * Q, img * Q, img * Q, kOutside);
+        float4 rw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (inimg) {
+          float rho = FADD(para_l, (float)(k - R));
+          rho = (rho != rho) ? rho : fminf(fmaxf(rho, 1e-6f), 1e6f);
+          const float div = FDIV(e.s, rho);
+          const float ex = FDIV(e.dx, div), ey = FDIV(e.dy, div);
+          const float flx = FSUB(FADD(e.px, ex), e.sx);
+          const float fly = FSUB(FADD(e.py, ey), e.sy);
+          const float qy = FADD((float)y, fly), qx = FADD((float)x, flx);
+          Tap bt;
+          if (MODE != kGather || a.idx_dbg) {
+            const float cqx = clip_keep_nan(qx, (float)(W - 1)), cqy = clip_keep_nan(qy, (float)(H - 1));
+            bt = make_tap(cqx, cqy, W, H);
+            if (a.idx_dbg) {
+              int4 v = bt.inside ? make_int4(bt.x0, bt.x0 + bt.dxo, bt.y0, bt.y0 + bt.dyo) : make_int4(-1, -1, -1, -1);
+              reinterpret_cast<int4*>(a.idx_dbg)[(size_t)p * K + k] = v;
+            }
+          }
+          if (MODE == kGather) {
+            if (qx == qx && qy == qy) {
+              const float fx0 = fminf(fmaxf(0.f, floorf(qx)), (float)(W - 2));
+              const float fy0 = fminf(fmaxf(0.f, floorf(qy)), (float)(H - 2));
+              const float ax = fminf(fmaxf(FSUB(qx, fx0), 0.f), 1.f);
+              const float ay = fminf(fmaxf(FSUB(qy, fy0), 0.f), 1.f);
+              ri = make_uint4((img + (uint32_t)((int)fy0 * W + (int)fx0)) * (uint32_t)Q, __float_as_uint(ax), __float_as_uint(ay), 1u);
+            }
+          } else if (bt.inside) {
+            tap_weights(bt.wx, bt.wy, rw.x, rw.y, rw.z, rw.w);
+            const uint32_t base = (img + (uint32_t)(bt.y0 * W + bt.x0)) * (uint32_t)Q;
+            ri.x = base;
+            ri.y = base + (uint32_t)bt.dxo * Q;
+            ri.z = base + (uint32_t)bt.dyo * wa.WQ;
+            ri.w = ri.z + (uint32_t)bt.dxo * Q;
+          }
+          const bool want_pd = a.prev_disp != nullptr;
+          const bool want_cl = a.centre_log != nullptr && k == R;
+          if (want_pd || want_cl) {                                    // warped previous parallax (:268, :280)
+            TapRec t;
+            rec_to_tap<MODE, Q>(ri, rw, wa.WQ, t);
+            const float pd = sample_scalar<MODE>(a.para_t, t, Q);
+            if (want_pd) a.prev_disp[(size_t)p * a.pd_stride + k] = pd;
+            if (want_cl) a.centre_log[(size_t)p * a.cl_stride] = logf(FMUL(pd, a.cl_scale));     // m4depth_network.py:238
+          }
+        }
+        recs[(lane * K + k) * RECW] = ri;
+        if (MODE != kGather)
+          recs[(lane * K + k) * RECW + 1] = make_uint4(__float_as_uint(rw.x), __float_as_uint(rw.y), __float_as_uint(rw.z), __float_as_uint(rw.w));
+      }
+    }
+    __syncwarp();
+
+    // ---- phases 1 and 2
+    uint4 iv[3];
+    float4 T[3][4];
+    // (record, taps) of hypothesis k_ of the item whose record slice starts at rp_ and whose quad pointer is cq_ -> buffer b_
+#define M4D_W_LOAD(b_, rp_, cq_, k_)                                                                           \
+    do {                                                                                                       \
+      uint4& v_ = iv[b_];                                                                                      \
+      float4* t_ = T[b_];                                                                                      \
+      v_ = lds128((rp_) + (k_) * RECW * 16);                                                                   \
+      if (MODE == kGather) {                                                                                   \
+        const unsigned char* p0 = (cq_) + (size_t)v_.x * 16u;                                                  \
+        const unsigned char* p1 = p0 + row_bytes;                                                              \
+        t_[0] = __ldg(reinterpret_cast<const float4*>(p0)); t_[1] = __ldg(reinterpret_cast<const float4*>(p0 + C * 4)); \
+        t_[2] = __ldg(reinterpret_cast<const float4*>(p1)); t_[3] = __ldg(reinterpret_cast<const float4*>(p1 + C * 4)); \
+      } else {                                                                                                 \
+        const uint32_t i11 = v_.w != kOutside ? v_.w : v_.x;                                                   \
+        t_[0] = __ldg(reinterpret_cast<const float4*>((cq_) + (size_t)v_.x * 16u));                            \
+        t_[1] = __ldg(reinterpret_cast<const float4*>((cq_) + (size_t)v_.y * 16u));                            \
+        t_[2] = __ldg(reinterpret_cast<const float4*>((cq_) + (size_t)v_.z * 16u));                            \
+        t_[3] = __ldg(reinterpret_cast<const float4*>((cq_) + (size_t)i11 * 16u));                             \
+      }                                                                                                        \
+    } while (0)
+
+    // item of pass gp: (pixel pl, quad q); its c1 quad, record slice and c2 quad pointer
+    int pl = lane / Q, q = lane - pl * Q;
+    uint32_t rp = recs_s + (uint32_t)(pl * K * RECW * 16);
+    const unsigned char* cq = c2b + q * 16;
+    auto c1_of = [&](int pl_, int q_) -> float4 {
+      const int xx = min(x_base + (pl_ & 7), W - 1), yy = min(y_base + (pl_ >> 3), H - 1);
+      return __ldg(c1v + (size_t)(img + (uint32_t)(yy * W + xx)) * Q + q_);
+    };
+    float4 cc = c1_of(pl, q);
+    M4D_W_LOAD(0, rp, cq, 0);
+    M4D_W_LOAD(1, rp, cq, 1);
+#pragma unroll 1
+    for (int gp = 0; gp < Q; ++gp) {
+      // next pass' item (prefetched from k = 7 on)
+      const int item_n = (gp + 1) * 32 + lane;
+      const int pl_n = item_n / Q, q_n = item_n - pl_n * Q;
+      const uint32_t rp_n = recs_s + (uint32_t)(pl_n * K * RECW * 16);
+      const unsigned char* cq_n = c2b + q_n * 16;
+      const bool more = gp + 1 < Q;
+      const __half2 h01 = __floats2half2_rn(cc.x, cc.y), h23 = __floats2half2_rn(cc.z, cc.w);     // :276 tf.cast(c1, fp16)
+      if (more) cc = c1_of(pl_n, q_n);
+      float* my_part = part + ((gp % RP) * 32 + lane) * K;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (k + 2 < K) M4D_W_LOAD((k + 2) % 3, rp, cq, k + 2);
+        else if (more) M4D_W_LOAD((k + 2) % 3, rp_n, cq_n, k + 2 - K);
+        const uint4 v = iv[k % 3];
+        const float4 t00 = T[k % 3][0], t01 = T[k % 3][1], t10 = T[k % 3][2], t11 = T[k % 3][3];
+        const bool valid = (MODE == kGather) ? (v.w != 0u) : (v.w != kOutside);
+        const u64 a00 = pk(t00.x, t00.y), b00 = pk(t00.z, t00.w), a01 = pk(t01.x, t01.y), b01 = pk(t01.z, t01.w);
+        const u64 a10 = pk(t10.x, t10.y), b10 = pk(t10.z, t10.w), a11 = pk(t11.x, t11.y), b11 = pk(t11.z, t11.w);
+        u64 va, vb;
+        if (MODE == kGather) {
+          const float axf = __uint_as_float(v.y), ayf = __uint_as_float(v.z);
+          const u64 ax = pk(axf, axf), ay = pk(ayf, ayf);
+          // top = ax*(TR-TL)+TL ; bot = ax*(BR-BL)+BL ; out = ay*(bot-top)+top, every op rounded (dense_image_warp.py:188-190);
+          // the multiply is fma(x, y, -0) with an opaque -0 so that ptxas cannot contract it with the following add.
+          const u64 topa = add2(fma2(ax, sub2(a01, a00), NZ2), a00);
+          const u64 bota = add2(fma2(ax, sub2(a11, a10), NZ2), a10);
+          va = add2(fma2(ay, sub2(bota, topa), NZ2), topa);
+          const u64 topb = add2(fma2(ax, sub2(b01, b00), NZ2), b00);
+          const u64 botb = add2(fma2(ax, sub2(b11, b10), NZ2), b10);
+          vb = add2(fma2(ay, sub2(botb, topb), NZ2), topb);
+        } else {
+          const uint4 wv = lds128(rp + (k * RECW + 1) * 16);
+          const float w0 = __uint_as_float(wv.x), w1 = __uint_as_float(wv.y), w2 = __uint_as_float(wv.z), w3 = __uint_as_float(wv.w);
+          const u64 w00 = pk(w0, w0), w01 = pk(w1, w1), w10 = pk(w2, w2), w11 = pk(w3, w3);
+          if (MODE == kBP) {
+            va = add2(add2(add2(fma2(a00, w00, NZ2), fma2(a01, w01, NZ2)), fma2(a10, w10, NZ2)), fma2(a11, w11, NZ2));
+            vb = add2(add2(add2(fma2(b00, w00, NZ2), fma2(b01, w01, NZ2)), fma2(b10, w10, NZ2)), fma2(b11, w11, NZ2));
+          } else {
+            va = fma2(a11, w11, fma2(a10, w10, fma2(a01, w01, fma2(a00, w00, NZ2))));
+            vb = fma2(b11, w11, fma2(b10, w10, fma2(b01, w01, fma2(b00, w00, NZ2))));
+          }
+        }
+        float v0, v1, v2, v3;
+        upk(va, v0, v1);
+        upk(vb, v2, v3);
+        const __half2 p01 = __hmul2(h01, __floats2half2_rn(v0, v1));      // :276 fp16 operands, fp16 product
+        const __half2 p23 = __hmul2(h23, __floats2half2_rn(v2, v3));
+        const float sk = sum4_h(h2_bits(p01), h2_bits(p23));
+        my_part[k] = valid ? sk : 0.f;
+      }
+      rp = rp_n; cq = cq_n;
+      if ((gp + 1) % RP == 0) {
+        // ---- phase 2: group means of the PH pixels just finished -> cv, cut-major channel = cut*K + k (:277-278)
+        __syncwarp();
+        constexpr int OUTS = PH * CUTS * K;
+        constexpr int GW = C / CUTS;
+        const int pl0 = (gp / RP) * PH;
+#pragma unroll
+        for (int j = 0; j < (OUTS + 31) / 32; ++j) {
+          const int it = j * 32 + lane;
+          if (OUTS % 32 == 0 || it < OUTS) {
+            const int plr = it / (CUTS * K), rem = it - plr * (CUTS * K);
+            const int cut = rem / K, k = rem - cut * K;
+            const float* src = part + (plr * Q + cut * GQ) * K + k;
+            float acc = src[0];
+#pragma unroll
+            for (int g = 1; g < GQ; ++g) acc = FADD(acc, src[g * K]);
+            const float mean = (GW & (GW - 1)) == 0 ? FMUL(acc, 1.0f / (float)GW) : FDIV(acc, (float)GW);
+            const int px = x_base + ((pl0 + plr) & 7), py = y_base + ((pl0 + plr) >> 3);
+            if (px < W && py < H)
+              a.cv[(size_t)(img + (uint32_t)(py * W + px)) * a.cv_stride + rem] = __half2float(__float2half_rn(mean));
+          }
+        }
+        __syncwarp();
+      }
+    }
+#undef M4D_W_LOAD
+    __syncwarp();
+  }
+}
+
+template <int C, int CUTS>
+static cudaError_t launch_warp(WArgs& wa, int interp, int ctas_per_sm, cudaStream_t st) {
+  typedef WCfg<C> Cfg;
+  const PscvArgs& a = wa.a;
+  wa.tiles_x = (a.w + 7) / 8;
+  wa.tiles_y = (a.h + 3) / 4;
+  wa.sup_x = (wa.tiles_x + 1) / 2;
+  wa.sup_y = (wa.tiles_y + 1) / 2;
+  wa.n_sup = wa.sup_x * wa.sup_y * a.b;
+  cudaError_t e = cudaSuccess;
+#define M4D_PSCVW_LAUNCH(MODE, RECW)                                                                            \
+  do {                                                                                                          \
+    const size_t smem = 4 * (size_t)Cfg::warp_bytes(RECW);                                                      \
+    int grid = m4d_sm_count() * ctas_per_sm;                                                                    \
+    if (grid > wa.n_sup) grid = wa.n_sup;                                                                       \
+    e = cudaFuncSetAttribute(pscv9w_kernel<C, CUTS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) pscv9w_kernel<C, CUTS, MODE><<<grid, 128, smem, st>>>(wa);                            \
+  } while (0)
+  if (interp == kGather) M4D_PSCVW_LAUNCH(kGather, 1);
+  else if (interp == kBP) M4D_PSCVW_LAUNCH(kBP, 2);
+  else M4D_PSCVW_LAUNCH(kBPFma, 2);
+#undef M4D_PSCVW_LAUNCH
+  return e;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -579,7 +847,9 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
   M4D_REQUIRE(search_range >= 0 && search_range <= 8, "m4d_pscv_fused_fwd: search_range must be in [0,8] (got %d)", search_range);
   M4D_REQUIRE(c % cuts == 0 && (c / cuts) % 4 == 0, "m4d_pscv_fused_fwd: group width c/cuts must be a multiple of 4 (c=%d cuts=%d)", c, cuts);
   const bool force_generic = (interp & M4D_INTERP_FLAG_GENERIC) != 0;
-  interp &= ~M4D_INTERP_FLAG_GENERIC;
+  const bool force_tile = (interp & M4D_INTERP_FLAG_TILE) != 0;
+  const int ctas_override = (interp >> 12) & 0xF;                  // tuning experiments only (tools/microbench.py)
+  interp &= 0xFF;
   M4D_REQUIRE(interp >= 0 && interp <= 2, "m4d_pscv_fused_fwd: bad interp mode %d", interp);
   M4D_REQUIRE(interp != kGather || (h >= 2 && w >= 2), "m4d_pscv_fused_fwd: the gather convention needs h,w >= 2");
   M4D_REQUIRE(aligned16(c1) && aligned16(c2), "m4d_pscv_fused_fwd: feature maps must be 16-byte aligned");
@@ -604,6 +874,31 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool fast_c = c == 16 || c == 32 || c == 64 || c == 96 || c == 128 || c == 192;
+  // network (c, cuts) pairs (m4depth_network.py:59,174): the warp-autonomous kernel
+  if (search_range == 4 && !force_generic && !force_tile) {
+    WArgs wa;
+    wa.a = a;
+    wa.WQ = (uint32_t)w * (uint32_t)a.Q;
+    const int cps = ctas_override ? ctas_override : 0;
+    bool hit = true;
+    switch (c * 16 + cuts) {
+      case 16 * 16 + 1:  e = launch_warp<16, 1>(wa, interp, cps ? cps : 4, st); break;
+      case 32 * 16 + 2:  e = launch_warp<32, 2>(wa, interp, cps ? cps : 4, st); break;
+      case 64 * 16 + 2:  e = launch_warp<64, 2>(wa, interp, cps ? cps : 4, st); break;
+      case 96 * 16 + 4:  e = launch_warp<96, 4>(wa, interp, cps ? cps : 4, st); break;
+      case 128 * 16 + 4: e = launch_warp<128, 4>(wa, interp, cps ? cps : 4, st); break;
+      case 192 * 16 + 8: e = launch_warp<192, 8>(wa, interp, cps ? cps : 4, st); break;
+      default: hit = false;
+    }
+    if (hit) {
+      if (e != cudaSuccess) {
+        m4d_set_error("m4d_pscv_fused_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return M4D_ECUDA;
+      }
+      M4D_CHECK_LAUNCH("m4d_pscv_fused_fwd");
+      return M4D_OK;
+    }
+  }
   if (search_range == 4 && fast_c && b <= 65535 && !force_generic) {
     FastArgs fa;
     fa.a = a;

@@ -114,8 +114,8 @@ def test_pscv_golden(golden_dir, case, branch):
                                    (1, 37, 53, 16, 1), (1, 9, 33, 64, 2), (1, 12, 16, 96, 3), (1, 7, 9, 64, 1)])
 @pytest.mark.parametrize("interp", [0, 1, 2])
 def test_pscv_specialised_kernel_equals_generic_kernel(shape, interp):
-    """The K=9 specialised kernel (2-D tiles, partial tiles at the borders, every pyramid channel count, odd group
-    counts) is bit-identical to the shape-generic kernel, including prev_disp, the tap grids and the fused
+    """The K=9 kernels - warp-autonomous (the network's (c, cuts) pairs) and CTA-tile (2-D tiles, partial tiles at the
+    borders, every pyramid channel count, odd group counts) - are bit-identical to the shape-generic kernel, including prev_disp, the tap grids and the fused
     log(centre) output the pipeline consumes."""
     m = _m4d()
     L = m._lib
@@ -126,7 +126,7 @@ def test_pscv_specialised_kernel_equals_generic_kernel(shape, interp):
     args = [cu(x) for x in (c1, c2, pt, pl, rot, trans)]
     dc = dev_cam(cam)
     res = []
-    for flag in (0, L.INTERP_FLAG_GENERIC):
+    for flag in (0, L.INTERP_FLAG_TILE, L.INTERP_FLAG_GENERIC):
         cv, pd, idx = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=interp | flag, return_index_grids=True)
         xs = cuts * 9 + 3
         wide = torch.full((b, h, w, xs), -7.0, device="cuda")
@@ -135,9 +135,10 @@ def test_pscv_specialised_kernel_equals_generic_kernel(shape, interp):
             L.ptr(dc["c"]), b, h, w, c, cuts, 4, wide.data_ptr() + 4, xs, None, 0, wide.data_ptr() + 4 * (xs - 1), xs, 0.5,
             None, interp | flag, L.stream()))
         res.append((cv.cpu(), pd.cpu(), idx.cpu(), wide.cpu()))
-    for a_, b_ in zip(*res):
-        assert torch.equal(a_.view(torch.int32) if a_.dtype == torch.float32 else a_,
-                           b_.view(torch.int32) if b_.dtype == torch.float32 else b_)
+    for other in res[1:]:
+        for a_, b_ in zip(res[0], other):
+            assert torch.equal(a_.view(torch.int32) if a_.dtype == torch.float32 else a_,
+                               b_.view(torch.int32) if b_.dtype == torch.float32 else b_)
     cv, pd, _, wide = res[0]
     assert torch.equal(wide[..., 1:1 + cuts * 9], cv) and torch.all(wide[..., 0] == -7.0) and torch.all(wide[..., cuts * 9 + 1] == -7.0)
     want = torch.log(pd[..., 4] * 0.5)

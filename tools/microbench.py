@@ -67,7 +67,10 @@ def pscv(b=8):
             L.check(L.lib.m4d_pscv_fused_fwd_ex(L.ptr(c1), L.ptr(c2), L.ptr(pt), L.ptr(pl), L.ptr(rot), 4, L.ptr(trans), L.ptr(cam["f"]),
                                                 L.ptr(cam["c"]), b, h, w, c, cuts, 4, L.ptr(cv), 9 * cuts, L.ptr(pd) if p9 else None, 9,
                                                 None if p9 else L.ptr(cl), 1, 0.5, None, mode, st))
-        for mode, name in ((0, "gather"), (1, "bp"), (2, "bp_fma"), (0x100, "gather/generic")):
+        variants = [(0, "gather"), (1, "bp"), (2, "bp_fma"), (0x200, "gather/tile"), (0x100, "gather/generic")]
+        if os.environ.get("CPS"):
+            variants = [(int(c) << 12, f"gather/cps{c}") for c in os.environ["CPS"].split(",")] + [(0x200, "gather/tile")]
+        for mode, name in variants:
             for p9 in (True, False):
                 med, mn = timeit(lambda: raw(mode, p9))
                 nb = bytes_p9 if p9 else bytes_p1
