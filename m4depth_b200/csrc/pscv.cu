@@ -574,10 +574,13 @@ static cudaError_t launch_fast(const FastArgs& fa, int interp, cudaStream_t st) 
 //   phase 2   every PH pixels: ordered group sums from the warp's partial-sum slice, mean, fp16 round, coalesced stores
 // Only __syncwarp() separates the phases.  The grid is persistent (a multiple of the SM count); a CTA walks 16x8-pixel
 // super tiles (its four warps take the four 8x4 quadrants) so that concurrently gathered c2 rows share L1 lines.
-template <int C>
+template <int C, int VAR>
 struct WCfg {
   static constexpr int Q = C / 4;
-  static constexpr int PH = Q <= 4 ? 32 : Q == 8 ? 16 : Q == 16 ? 8 : Q == 24 ? 4 : Q == 32 ? 4 : 2;   // pixels per phase-2 round
+  static constexpr int DIST = (VAR == 1 || VAR == 2) ? 1 : 2;                  // tap prefetch distance (hypotheses)
+  static constexpr int MINB = VAR == 0 ? 3 : VAR == 1 ? 5 : VAR == 2 ? 6 : 4;  // resident CTAs per SM the registers allow
+  static constexpr int PH0 = Q <= 4 ? 32 : Q == 8 ? 16 : Q == 16 ? 8 : Q == 24 ? 4 : Q == 32 ? 4 : 2;
+  static constexpr int PH = (VAR != 0 && Q <= 8) ? PH0 / 2 : PH0;              // pixels per phase-2 round
   static constexpr int ROUND_PASSES = PH * Q / 32;
   static_assert(PH * Q % 32 == 0 && 32 % PH == 0, "round");
   static constexpr int part_bytes = ROUND_PASSES * 32 * 9 * 4;
@@ -592,9 +595,10 @@ struct WArgs {
   uint32_t WQ;
 };
 
-template <int C, int CUTS, int MODE>
-__global__ void __launch_bounds__(128, 3) pscv9w_kernel(WArgs wa) {
-  typedef WCfg<C> Cfg;
+template <int C, int CUTS, int MODE, int VAR>
+__global__ void __launch_bounds__(128, WCfg<C, VAR>::MINB) pscv9w_kernel(WArgs wa) {
+  typedef WCfg<C, VAR> Cfg;
+  constexpr int DIST = Cfg::DIST;
   constexpr int K = 9, R = 4, Q = Cfg::Q, GQ = Q / CUTS, PH = Cfg::PH, RP = Cfg::ROUND_PASSES;
   constexpr int RECW = (MODE == kGather) ? 1 : 2;
   constexpr int REC_BYTES = 32 * K * 16 * RECW;
@@ -719,7 +723,7 @@ __global__ void __launch_bounds__(128, 3) pscv9w_kernel(WArgs wa) {
     };
     float4 cc = c1_of(pl, q);
     M4D_W_LOAD(0, rp, cq, 0);
-    M4D_W_LOAD(1, rp, cq, 1);
+    if (DIST == 2) M4D_W_LOAD(1, rp, cq, 1);
 #pragma unroll 1
     for (int gp = 0; gp < Q; ++gp) {
       // next pass' item (prefetched from k = 7 on)
@@ -733,8 +737,8 @@ __global__ void __launch_bounds__(128, 3) pscv9w_kernel(WArgs wa) {
       float* my_part = part + ((gp % RP) * 32 + lane) * K;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        if (k + 2 < K) M4D_W_LOAD((k + 2) % 3, rp, cq, k + 2);
-        else if (more) M4D_W_LOAD((k + 2) % 3, rp_n, cq_n, k + 2 - K);
+        if (k + DIST < K) M4D_W_LOAD((k + DIST) % 3, rp, cq, k + DIST);
+        else if (more) M4D_W_LOAD((k + DIST) % 3, rp_n, cq_n, k + DIST - K);
         const uint4 v = iv[k % 3];
         const float4 t00 = T[k % 3][0], t01 = T[k % 3][1], t10 = T[k % 3][2], t11 = T[k % 3][3];
         const bool valid = (MODE == kGather) ? (v.w != 0u) : (v.w != kOutside);
@@ -803,9 +807,10 @@ __global__ void __launch_bounds__(128, 3) pscv9w_kernel(WArgs wa) {
   }
 }
 
-template <int C, int CUTS>
+template <int C, int CUTS, int VAR>
 static cudaError_t launch_warp(WArgs& wa, int interp, int ctas_per_sm, cudaStream_t st) {
-  typedef WCfg<C> Cfg;
+  typedef WCfg<C, VAR> Cfg;
+  if (ctas_per_sm <= 0) ctas_per_sm = Cfg::MINB;
   const PscvArgs& a = wa.a;
   wa.tiles_x = (a.w + 7) / 8;
   wa.tiles_y = (a.h + 3) / 4;
@@ -818,8 +823,8 @@ static cudaError_t launch_warp(WArgs& wa, int interp, int ctas_per_sm, cudaStrea
     const size_t smem = 4 * (size_t)Cfg::warp_bytes(RECW);                                                      \
     int grid = m4d_sm_count() * ctas_per_sm;                                                                    \
     if (grid > wa.n_sup) grid = wa.n_sup;                                                                       \
-    e = cudaFuncSetAttribute(pscv9w_kernel<C, CUTS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e == cudaSuccess) pscv9w_kernel<C, CUTS, MODE><<<grid, 128, smem, st>>>(wa);                            \
+    e = cudaFuncSetAttribute(pscv9w_kernel<C, CUTS, MODE, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e == cudaSuccess) pscv9w_kernel<C, CUTS, MODE, VAR><<<grid, 128, smem, st>>>(wa);                       \
   } while (0)
   if (interp == kGather) M4D_PSCVW_LAUNCH(kGather, 1);
   else if (interp == kBP) M4D_PSCVW_LAUNCH(kBP, 2);
@@ -879,15 +884,13 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
     WArgs wa;
     wa.a = a;
     wa.WQ = (uint32_t)w * (uint32_t)a.Q;
-    const int cps = ctas_override ? ctas_override : 0;
+    const int cps = ctas_override;
     bool hit = true;
+    // measured on B200 (tools/microbench.py pscv, b=8): 175 vs 192 us at level 1, 86 vs 92 us at level 2; from c = 64 on a
+    // pixel is a whole pass or more, a warp task becomes a long serial chain and the CTA-tile kernel is faster.
     switch (c * 16 + cuts) {
-      case 16 * 16 + 1:  e = launch_warp<16, 1>(wa, interp, cps ? cps : 4, st); break;
-      case 32 * 16 + 2:  e = launch_warp<32, 2>(wa, interp, cps ? cps : 4, st); break;
-      case 64 * 16 + 2:  e = launch_warp<64, 2>(wa, interp, cps ? cps : 4, st); break;
-      case 96 * 16 + 4:  e = launch_warp<96, 4>(wa, interp, cps ? cps : 4, st); break;
-      case 128 * 16 + 4: e = launch_warp<128, 4>(wa, interp, cps ? cps : 4, st); break;
-      case 192 * 16 + 8: e = launch_warp<192, 8>(wa, interp, cps ? cps : 4, st); break;
+      case 16 * 16 + 1: e = launch_warp<16, 1, 1>(wa, interp, cps, st); break;
+      case 32 * 16 + 2: e = launch_warp<32, 2, 1>(wa, interp, cps, st); break;
       default: hit = false;
     }
     if (hit) {

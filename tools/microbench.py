@@ -69,7 +69,7 @@ def pscv(b=8):
                                                 None if p9 else L.ptr(cl), 1, 0.5, None, mode, st))
         variants = [(0, "gather"), (1, "bp"), (2, "bp_fma"), (0x200, "gather/tile"), (0x100, "gather/generic")]
         if os.environ.get("CPS"):
-            variants = [(int(c) << 12, f"gather/cps{c}") for c in os.environ["CPS"].split(",")] + [(0x200, "gather/tile")]
+            variants = [((int(c[0]) << 16) | (int(c[1:] or 0) << 12), f"gather/var{c[0]}cps{c[1:]}") for c in os.environ["CPS"].split(",")] + [(0x200, "gather/tile")]
         for mode, name in variants:
             for p9 in (True, False):
                 med, mn = timeit(lambda: raw(mode, p9))
