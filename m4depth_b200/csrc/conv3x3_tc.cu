@@ -44,8 +44,45 @@ struct TcArgs {
   int nb;                           // weight-slab stages that fit in shared memory (3 at Cout = 128 ... 6)
   int nacc, nsets;                  // TMEM accumulators per tile (2 or 4) and accumulator sets (2 = epilogue overlaps the next tile)
   int tma_out;                      // epilogue through TMA stores (ys % 4 == 0 and y 16-byte aligned), else scalar stores
+  int concat;                       // Cout <= 64: hi*hi and hi*lo in ONE MMA of N = 2*Cout over the adjacent [hi|lo] weight planes
+  int s2d_c;                        // 0: stride 1.  C > 0: stride-2 conv over C input channels as a 2x2-cell conv (see below)
+  int s2d_chunks;                   // 32-channel chunks of one input row pair's (px, c) range = 2C / 32
   float alpha;
 };
+
+// Stride 2 (FeaturePyramid's down-sampling convs, m4depth_network.py:66-72, even input sizes: TF SAME pads bottom / right
+// only).  out[oy,ox] = sum_{ky,kx} x[2oy+ky, 2ox+kx] * w[ky,kx]  is a stride-1 conv over 2x2-pixel CELLS: input row
+// 2(oy+dy)+py, column 2(ox+dx)+px with ky = 2dy+py, kx = 2dx+px, cell offsets dy,dx in {0,1}.  A 5-D tensor map over the
+// NHWC tensor viewed as [b][H/2][py][W/2][(px,c)] lets ONE TMA load per k-block bring the same [18][10][32] halo as the
+// stride-1 kernel: k-block kb = (py, 32-channel chunk of the contiguous (px, c) range).  Cell offset (dy,dx) is tap
+// (dy+1, dx+1) of the 3x3 machinery; taps with a -1 offset, (dy=1, py=1) and (dx=1, px=1) carry no weights and are skipped
+// whole (k-block, tap) slabs or k-steps at a time, so the tensor cores do exactly the 9*C MACs per output of the conv.
+// (C is a multiple of 16 and a k-step is 8 channels, so the px = 0 channels of a k-block are a prefix of whole k-steps.)
+// The taps of k-block kb that carry weights: ky in [ky_lo, ky_hi], kx in [kx_lo, 2]; a tap uses the first nk(kx) k-steps.
+struct KbTaps {
+  int ky_lo, ky_hi, kx_lo;
+  int nks;      // k-steps (8 channels each) per tap; for the kx = 2 taps of the stride-2 formulation: nks2
+  int nks2;
+  __device__ __forceinline__ int nk(int kx) const { return kx == 2 ? nks2 : nks; }
+  __device__ __forceinline__ int kx_hi() const { return nks2 > 0 ? 2 : 1; }
+};
+template <bool S2D>
+__device__ __forceinline__ KbTaps kb_taps(const TcArgs& a, int kb) {
+  KbTaps t;
+  if (!S2D) {
+    const int rem = a.cin - kb * KC;
+    t.nks = t.nks2 = rem >= KC ? KC / 8 : (rem + 7) >> 3;          // 16-channel inputs: 2 of the 4 k-steps are zero fill
+    t.ky_lo = 0; t.ky_hi = 2; t.kx_lo = 0;
+  } else {
+    const int py = kb / a.s2d_chunks;
+    const int ch0 = (kb - py * a.s2d_chunks) * KC;                 // first (px, c) index of this k-block; px = index / C
+    const int left = a.s2d_c - ch0;                                // channels of this k-block that belong to px = 0
+    t.nks = KC / 8;
+    t.nks2 = left <= 0 ? 0 : (left >= KC ? KC / 8 : (left + 7) >> 3);
+    t.ky_lo = 1; t.ky_hi = py ? 1 : 2; t.kx_lo = 1;
+  }
+  return t;
+}
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -72,6 +109,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -153,6 +196,7 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 // All rings run across tile boundaries, so the loads and the split of tile i+1 and the whole epilogue of tile i overlap
 // with the MMAs (measured before this structure: 30 % of a 128-column tile was un-overlapped prologue + epilogue,
 // profiles/r1f_conv_tc_tile_phases.md).
+template <bool S2D, bool CONCAT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_y, TcArgs a) {
@@ -169,7 +213,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t tmem_slot = acc_empty + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = a.kblocks, NB = a.nb, NSETS = a.nsets;
+  const int KB = a.kblocks, NB = a.nb;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
@@ -213,7 +257,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_wait(a_empty + 8 * s, ((ka / A_STAGES) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full + 8 * s, A_BYTES);
-          tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
+          if (!S2D) {
+            tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
+          } else {
+            const int py = kb / a.s2d_chunks;
+            tma_load_5d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, (kb - py * a.s2d_chunks) * KC, ox0 - 1, py, oy0 - 1, bi);
+          }
         }
         __syncwarp();
       }
@@ -223,28 +272,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     int it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
-      for (int kt = 0; kt < KB * 9; ++kt, ++it) {
-        const int s = it % NB;
-        mbar_wait(b_empty + 8 * s, ((it / NB) & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
-          tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, kt * 2 * a.cout);
-        }
-        __syncwarp();
+      for (int kb = 0; kb < KB; ++kb) {
+        const KbTaps tp = kb_taps<S2D>(a, kb);
+        for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky)
+          for (int kx = tp.kx_lo; kx <= tp.kx_hi(); ++kx, ++it) {
+            const int s = it % NB;
+            mbar_wait(b_empty + 8 * s, ((it / NB) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
+              tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, (kb * 9 + ky * 3 + kx) * 2 * a.cout);
+            }
+            __syncwarp();
+          }
       }
   } else if (warp == 2) {
     // ===== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*Cout
     const uint32_t lo_off16 = ((uint32_t)a.cout * 128u) >> 4;
     // The tensor core adds every K=8 partial product to the fp32 accumulator with TRUNCATION, so the error is biased and
     // grows with the number of additions made at full magnitude (one accumulator per tile: 1e-5 of the scale at cin = 128,
-    // and the bias survives into the depth maps).  Three measures keep the kernel in the FFMA class: every k-block starts
-    // fresh accumulators that the epilogue warps add in registers (round to nearest); the two small cross terms, whose
-    // truncation errors are 2^-11 smaller, have their own accumulator; and where TMEM has room (Cout <= 64) the hi*hi
-    // products are spread over three accumulators by tap column.
+    // and the bias survives into the depth maps).  Two measures keep the kernel in the FFMA class: every k-block starts
+    // fresh accumulators that the epilogue warps add in registers (round to nearest), and the small cross terms, whose
+    // truncation errors are 2^-11 smaller, have their own accumulators.
+    // Accumulator set (TMEM columns from d_set):  Cout > 64:  [hi*hi | lo*hi + hi*lo]           three MMAs per k-step
+    //                                             Cout <= 64: [hi*hi | hi*lo | lo*hi]           two MMAs per k-step: A_hi against
+    // the adjacent [W_hi ; W_lo] planes as one N = 2*Cout operand.  With small N the MMAs are bound by the 4 KB A-operand
+    // read from shared memory (128 B/clk), so one A pass less per k-step is 25-30 % of the layer.
     const uint32_t ncol = (uint32_t)a.cout;
-    const uint32_t nmain = (uint32_t)a.nacc - 1u;
     int ka = 0, it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++ka) {
@@ -252,39 +308,45 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int set = ka & 1;
         mbar_wait(acc_empty + 8 * set, ((ka >> 1) & 1) ^ 1);            // epilogue has drained this set
         const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
-        const uint32_t d_corr = d_set + nmain * ncol;
+        const uint32_t d_corr = d_set + (CONCAT ? 2u : 1u) * ncol;
         const int sa = ka % A_STAGES;
         mbar_wait(a_ready + 8 * sa, (ka / A_STAGES) & 1);
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
         const uint64_t dA_hi = umma_desc(sA + sa * 2 * A_SLOT, HALO_W * 128);
         const uint64_t dA_lo = umma_desc(sA + sa * 2 * A_SLOT + A_SLOT, HALO_W * 128);
-        const int rem = a.cin - kb * KC;
-        const int nks = rem >= KC ? KC / 8 : (rem + 7) >> 3;               // 16-channel inputs: 2 of the 4 k-steps are zero fill
+        const KbTaps tp = kb_taps<S2D>(a, kb);
+        const int kx_hi = tp.kx_hi();
 #pragma unroll 1
-        for (int ky = 0; ky < 3; ++ky) {
+        for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky) {
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx, ++it) {
+          for (int kx = S2D ? 1 : 0; kx < 3; ++kx) {
+            if (S2D && kx > kx_hi) break;
+            const int nk = tp.nk(kx);
             const int sb = it % NB;
             mbar_wait(b_full + 8 * sb, (it / NB) & 1);
+            ++it;
             tc_fence_after();
             if (elect_one()) {
               const uint64_t dB_hi = umma_desc(sB + sb * b_stage_bytes, 1024);
               const uint32_t tap16 = (uint32_t)((ky * HALO_W + kx) * 128) >> 4;
-              const uint32_t jm = nmain == 3u ? (uint32_t)kx : 0u;
-              const uint32_t d_main = d_set + jm * ncol;
-              const uint32_t later = ky > 0 ? 1u : 0u;                     // past the first tap row of the k-block
-              const uint32_t main_started = (nmain == 3u || kx == 0) ? later : 1u;
+              const uint32_t later = (ky > tp.ky_lo || kx > (S2D ? 1 : 0)) ? 1u : 0u;     // past the first tap of the k-block
 #pragma unroll
               for (int ks = 0; ks < KC / 8; ++ks) {
-                if (ks >= nks) break;
+                if (ks >= nk) break;
                 const uint64_t a_hi = dA_hi + tap16 + ks * 2, a_lo = dA_lo + tap16 + ks * 2;
                 const uint64_t b_hi = dB_hi + ks * 2, b_lo = dB_hi + lo_off16 + ks * 2;
-                tc_mma_tf32(d_main, a_hi, b_hi, idesc, ks > 0 ? 1u : main_started);
-                tc_mma_tf32(d_corr, a_lo, b_hi, idesc, (ks > 0 || kx > 0) ? 1u : later);
-                tc_mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+                const uint32_t acc = ks > 0 ? 1u : later;
+                if (CONCAT) {
+                  tc_mma_tf32(d_set, a_hi, b_hi, idesc2, acc);
+                  tc_mma_tf32(d_corr, a_lo, b_hi, idesc, acc);
+                } else {
+                  tc_mma_tf32(d_set, a_hi, b_hi, idesc, acc);
+                  tc_mma_tf32(d_corr, a_lo, b_hi, idesc, acc);
+                  tc_mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+                }
               }
               tc_commit(b_empty + 8 * sb);
-              if (ky == 2 && kx == 2) {
+              if (ky == tp.ky_hi && kx == kx_hi) {
                 tc_commit(a_empty + 8 * sa);
                 tc_commit(acc_full + 8 * set);
               }
@@ -407,16 +469,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ weight packing
-// HWIO [3,3,cin,cout] -> [kb][tap][hi|lo][cout][32]: row ((kb*9+tap)*2+hl)*cout+co, column ci - 32*kb (zero beyond cin)
-__global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int cout_real, int cout, int kblocks, float* __restrict__ out) {
+// HWIO [3,3,cin,cout_total], output channels [co_off, co_off + cout_real) -> [kb][tap][hi|lo][cout][32]:
+// row ((kb*9+tap)*2+hl)*cout+co, column = channel within the k-block (zero beyond cin / beyond cout_real).
+// s2d_c > 0 (stride 2): k-block kb = (py, chunk), column -> (px, c); tap (dy+1, dx+1) holds w[2dy+py][2dx+px][c] (see kb_taps).
+__global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int cout_total, int co_off, int cout_real, int cout,
+                                       int kblocks, int s2d_c, int s2d_chunks, float* __restrict__ out) {
   const int64_t n = (int64_t)kblocks * 9 * cout * KC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % KC);
     const int co = (int)((i / KC) % cout);
     const int tap = (int)((i / ((int64_t)KC * cout)) % 9);
     const int kb = (int)(i / ((int64_t)KC * cout * 9));
-    const int ci = kb * KC + c;
-    const float v = (ci < cin && co < cout_real) ? w[((size_t)tap * cin + ci) * cout_real + co] : 0.f;
+    float v = 0.f;
+    if (co < cout_real) {
+      if (s2d_c == 0) {
+        const int ci = kb * KC + c;
+        if (ci < cin) v = w[((size_t)tap * cin + ci) * cout_total + co_off + co];
+      } else {
+        const int py = kb / s2d_chunks, idx = (kb - py * s2d_chunks) * KC + c;     // idx in the (px, c) range [0, 2C)
+        const int px = idx / s2d_c, ci = idx - px * s2d_c;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ky = 2 * dy + py, kx = 2 * dx + px;
+        if (dy >= 0 && dx >= 0 && ky <= 2 && kx <= 2 && px < 2) v = w[((size_t)(ky * 3 + kx) * cin + ci) * cout_total + co_off + co];
+      }
+    }
     uint32_t hi, lo, lo_r;
     split_tf32(__float_as_uint(v), hi, lo);
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo_r) : "f"(__uint_as_float(lo)));
@@ -442,51 +518,34 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-inline bool tc_shape_ok(int cin, int cout) { return cin >= 1 && cout >= 1 && cout <= 128; }
+// Output channels beyond 128 (the 192-channel encoder level) run as two launches over halves of the channels.
+inline int tc_nsplit(int cout) { return cout <= 128 ? 1 : 2; }
+inline bool tc_shape_ok(int cin, int cout, int stride) {
+  if (cin < 1 || cout < 1 || cout > 256 || (cout > 128 && cout % 2 != 0)) return false;
+  if (stride == 1) return true;
+  return stride == 2 && cin % 16 == 0;          // the (px, c) range of a cell row splits into whole 32-channel k-blocks
+}
 inline int tc_cout_pad(int cout) { return (cout + 15) / 16 * 16; }
-inline int tc_kblocks(int cin) { return (cin + KC - 1) / KC; }
-
-}  // namespace
-
-extern "C" {
-
-int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout) {
-  if (!tc_shape_ok(cin, cout)) return 0;
-  return (int64_t)tc_kblocks(cin) * 9 * 2 * tc_cout_pad(cout) * KC;
+inline int tc_kblocks(int cin, int stride) { return stride == 1 ? (cin + KC - 1) / KC : 2 * (2 * cin / KC); }
+inline int64_t tc_packed_half_floats(int cin, int cout_half, int stride) {
+  return (int64_t)tc_kblocks(cin, stride) * 9 * 2 * tc_cout_pad(cout_half) * KC;
 }
 
-int m4d_conv3x3_tc_pack(const float* kernel_hwio, int cin, int cout, float* packed, void* stream) {
-  M4D_REQUIRE(kernel_hwio && packed, "m4d_conv3x3_tc_pack: null pointer");
-  M4D_REQUIRE(tc_shape_ok(cin, cout), "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d (cout must be in [1,128])", cin, cout);
-  const int kb = tc_kblocks(cin);
-  const int cp = tc_cout_pad(cout);
-  const int64_t n = (int64_t)kb * 9 * cp * KC;
-  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, cp, kb, packed);
-  M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
-  return M4D_OK;
-}
-
-int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
-                       int cout, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
-  M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
-  M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
-  if (!tc_shape_ok(cin, cout) || x_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
-      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u)) {
-    m4d_set_error("m4d_conv3x3_tc_fwd: shape / alignment outside the tcgen05 path (cin=%d cout=%d xs=%d ys=%d)", cin, cout, x_pix_stride, y_pix_stride);
-    return M4D_ENOTSUP;
-  }
+// one launch: output channels [0, cout) of `packed` into y (already offset by the caller)
+int tc_launch(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin, int cout,
+              int stride, float leaky_alpha, float* y, int y_pix_stride, cudaStream_t stream) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled is not available from this driver");
     return M4D_ECUDA;
   }
-  const int kb = tc_kblocks(cin);
+  const int kb = tc_kblocks(cin, stride);
   const int cout_real = cout;
   const bool tma_out = y_pix_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15u);
   cout = tc_cout_pad(cout);                    // from here on: the MMA N / packed row count
+  const int oh = stride == 1 ? h : h / 2, ow = stride == 1 ? w : w / 2;
   CUtensorMap mx, mw, my;
-  {
+  if (stride == 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
     const cuuint64_t strides[3] = {(cuuint64_t)x_pix_stride * 4, (cuuint64_t)w * x_pix_stride * 4, (cuuint64_t)h * w * x_pix_stride * 4};
     const cuuint32_t box[4] = {KC, HALO_W, HALO_H, 1};
@@ -495,6 +554,19 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
+      return M4D_ECUDA;
+    }
+  } else {
+    // [b][H/2][py][W/2][(px, c)]: x_pix_stride == cin, so the two pixels of a cell row are 2*cin contiguous floats
+    const cuuint64_t ps = (cuuint64_t)cin * 4;
+    const cuuint64_t dims[5] = {(cuuint64_t)2 * cin, (cuuint64_t)ow, 2, (cuuint64_t)oh, (cuuint64_t)b};
+    const cuuint64_t strides[4] = {2 * ps, (cuuint64_t)w * ps, 2 * (cuuint64_t)w * ps, (cuuint64_t)h * w * ps};
+    const cuuint32_t box[5] = {KC, HALO_W, 1, HALO_H, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled(x, stride 2) failed with %d", (int)r);
       return M4D_ECUDA;
     }
   }
@@ -511,8 +583,8 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     }
   }
   if (tma_out) {
-    const cuuint64_t dims[4] = {(cuuint64_t)cout_real, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
-    const cuuint64_t strides[3] = {(cuuint64_t)y_pix_stride * 4, (cuuint64_t)w * y_pix_stride * 4, (cuuint64_t)h * w * y_pix_stride * 4};
+    const cuuint64_t dims[4] = {(cuuint64_t)cout_real, (cuuint64_t)ow, (cuuint64_t)oh, (cuuint64_t)b};
+    const cuuint64_t strides[3] = {(cuuint64_t)y_pix_stride * 4, (cuuint64_t)ow * y_pix_stride * 4, (cuuint64_t)oh * ow * y_pix_stride * 4};
     const cuuint32_t box[4] = {32, TILE_W, TILE_H, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&my, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -522,19 +594,23 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
       return M4D_ECUDA;
     }
   } else {
-    my = mx;                                   // unused by the kernel
+    my = mw;                                   // unused by the kernel
   }
   TcArgs a;
-  a.bias = bias; a.y = y; a.h = h; a.w = w; a.cout = cout; a.cout_real = cout_real; a.cin = cin; a.tma_out = tma_out ? 1 : 0;
+  a.bias = bias; a.y = y; a.h = oh; a.w = ow; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
-  a.tiles_x = (w + TILE_W - 1) / TILE_W;
-  a.tiles_y = (h + TILE_H - 1) / TILE_H;
+  a.s2d_c = stride == 1 ? 0 : cin;
+  a.s2d_chunks = stride == 1 ? 1 : 2 * cin / KC;
+  a.cin = stride == 1 ? cin : 4 * cin;
+  a.tiles_x = (ow + TILE_W - 1) / TILE_W;
+  a.tiles_y = (oh + TILE_H - 1) / TILE_H;
   const int64_t ntiles = (int64_t)a.tiles_x * a.tiles_y * b;
   M4D_REQUIRE(ntiles < (1ll << 30), "m4d_conv3x3_tc_fwd: too many tiles");
   a.ntiles = (int)ntiles;
-  // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block.  A set holds 4 accumulators (3 for hi*hi
-  // by tap column + 1 for the cross terms) where they fit (Cout <= 64), else 2.
-  a.nacc = cout <= 64 ? 4 : 2;
+  // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block; a set is [hi*hi | hi*lo | lo*hi] (Cout <= 64,
+  // two MMAs per k-step) or [hi*hi | cross terms] (three MMAs per k-step).
+  a.concat = cout <= 64 ? 1 : 0;
+  a.nacc = a.concat ? 3 : 2;
   a.nsets = 2;
   const size_t fixed = 1024 + (size_t)A_STAGES * 2 * A_SLOT + 2 * OUT_SLOT + 512;
   const size_t stage = (size_t)2 * cout * 128;
@@ -545,7 +621,10 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
   const size_t smem = fixed + (size_t)nb * stage;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) {
       m4d_set_error("m4d_conv3x3_tc_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return M4D_ECUDA;
@@ -553,9 +632,73 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
     attr_set = true;
   }
   const int grid = a.ntiles < m4d_sm_count() ? a.ntiles : m4d_sm_count();
-  conv3x3_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mx, mw, my, a);
+  if (stride == 1) {
+    if (a.concat) conv3x3_tc_kernel<false, true><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+    else conv3x3_tc_kernel<false, false><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+  } else {
+    if (a.concat) conv3x3_tc_kernel<true, true><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+    else conv3x3_tc_kernel<true, false><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+  }
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t m4d_conv3x3_tc_packed_floats_s(int cin, int cout, int stride) {
+  if (!tc_shape_ok(cin, cout, stride)) return 0;
+  const int ns = tc_nsplit(cout);
+  return ns * tc_packed_half_floats(cin, cout / ns, stride);
+}
+
+int m4d_conv3x3_tc_pack_s(const float* kernel_hwio, int cin, int cout, int stride, float* packed, void* stream) {
+  M4D_REQUIRE(kernel_hwio && packed, "m4d_conv3x3_tc_pack: null pointer");
+  M4D_REQUIRE(tc_shape_ok(cin, cout, stride),
+              "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d stride=%d (cout <= 256, even beyond 128; stride 2 needs cin %% 16 == 0)",
+              cin, cout, stride);
+  const int kb = tc_kblocks(cin, stride);
+  const int ns = tc_nsplit(cout), ch = cout / ns;
+  const int cp = tc_cout_pad(ch);
+  const int64_t n = (int64_t)kb * 9 * cp * KC;
+  const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+  for (int i = 0; i < ns; ++i) {
+    conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, i * ch, ch, cp, kb, stride == 1 ? 0 : cin,
+                                                                    stride == 1 ? 1 : 2 * cin / KC,
+                                                                    packed + i * tc_packed_half_floats(cin, ch, stride));
+    M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
+  }
+  return M4D_OK;
+}
+
+int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                         int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
+  M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
+  M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
+  const bool s2_ok = stride != 2 || (h % 2 == 0 && w % 2 == 0 && x_pix_stride == cin);
+  if (!tc_shape_ok(cin, cout, stride) || !s2_ok || x_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
+      (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u)) {
+    m4d_set_error("m4d_conv3x3_tc_fwd: shape / alignment outside the tcgen05 path (cin=%d cout=%d stride=%d h=%d w=%d xs=%d ys=%d)", cin, cout,
+                  stride, h, w, x_pix_stride, y_pix_stride);
+    return M4D_ENOTSUP;
+  }
+  const int ns = tc_nsplit(cout), ch = cout / ns;
+  for (int i = 0; i < ns; ++i) {
+    const int rc = tc_launch(x, x_pix_stride, packed + i * tc_packed_half_floats(cin, ch, stride), bias + i * ch, b, h, w, cin, ch, stride,
+                             leaky_alpha, y + i * ch, y_pix_stride, (cudaStream_t)stream);
+    if (rc != M4D_OK) return rc;
+  }
+  return M4D_OK;
+}
+
+int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout) { return m4d_conv3x3_tc_packed_floats_s(cin, cout, 1); }
+int m4d_conv3x3_tc_pack(const float* kernel_hwio, int cin, int cout, float* packed, void* stream) {
+  return m4d_conv3x3_tc_pack_s(kernel_hwio, cin, cout, 1, packed, stream);
+}
+int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                       int cout, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
+  return m4d_conv3x3_tc_fwd_s(x, x_pix_stride, packed, bias, b, h, w, cin, cout, 1, leaky_alpha, y, y_pix_stride, stream);
 }
 
 }  // extern "C"

@@ -79,12 +79,12 @@ class _Conv2D:
             raise L.M4DError(f"conv kernel must be [3,3,cin,{self.filters}], got {tuple(k.shape)}")
         self.kernel = k
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
-        # tensor-core path (stride-1 layers with cout <= 128): TF32 hi/lo planes packed once per layer
+        # tensor-core path (stride 1, or stride 2 with cin % 16 == 0; cout <= 256): TF32 hi/lo planes packed once per layer
         self.packed = None
-        n = L.lib.m4d_conv3x3_tc_packed_floats(k.shape[2], self.filters) if self.strides == 1 else 0
+        n = L.lib.m4d_conv3x3_tc_packed_floats_s(k.shape[2], self.filters, self.strides)
         if n > 0:
             self.packed = torch.empty(n, dtype=torch.float32, device=k.device)
-            L.check(L.lib.m4d_conv3x3_tc_pack(L.ptr(k), k.shape[2], self.filters, L.ptr(self.packed), L.stream()))
+            L.check(L.lib.m4d_conv3x3_tc_pack_s(L.ptr(k), k.shape[2], self.filters, self.strides, L.ptr(self.packed), L.stream()))
 
     def out_shape(self, x):
         b, h, w, _ = x.shape
@@ -105,18 +105,22 @@ class _Conv2D:
         xs, ys = _pix_stride(x), _pix_stride(out)
         algo = algo or DEFAULT_CONV_ALGO
         # algo: 0 = auto (tcgen05 3xTF32 where the layer was packed and the strides allow, else FFMA2), 1 = FFMA2, 2 = tcgen05
-        if algo != 1 and self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin:
+        tc_ok = self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin
+        if self.strides == 2:       # the 2x2-cell formulation: even sizes (TF SAME pads bottom / right only), dense pixels
+            tc_ok = tc_ok and h % 2 == 0 and w % 2 == 0 and xs == cin
+        if algo != 1 and tc_ok:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            L.check(L.lib.m4d_conv3x3_tc_fwd(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
-                                             float(alpha), L.ptr(out), ys, L.stream()))
+            L.check(L.lib.m4d_conv3x3_tc_fwd_s(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
+                                               self.strides, float(alpha), L.ptr(out), ys, L.stream()))
             if self.events is not None:
                 ev1.record()
                 self.events.append((ev0, ev1))
             return out
         if algo == 2:
-            raise L.M4DError("conv layer is outside the tcgen05 path (stride 1, cout <= 128, cin >= 16, input pixel stride % 4 == 0)")
+            raise L.M4DError("conv layer is outside the tcgen05 path (cout <= 256, cin >= 16, input pixel stride % 4 == 0; "
+                             "stride 2: even sizes, cin % 16 == 0, dense pixels)")
         L.check(L.lib.m4d_conv3x3_nhwc(L.ptr(x), xs, L.ptr(self.kernel), L.ptr(self.bias), b, h, w, cin,
                                        self.filters, self.strides, float(alpha), L.ptr(out), ys, 1, L.stream()))
         return out

@@ -409,6 +409,56 @@ def test_conv3x3_tcgen05_3xtf32_vs_oracle(cfg):
     assert e_tc < 4e-6
 
 
+@pytest.mark.parametrize("cfg", [(2, 32, 48, 16, 16), (1, 24, 80, 32, 32), (1, 20, 36, 64, 64), (2, 12, 40, 96, 96),
+                                 (1, 12, 40, 128, 128), (1, 12, 40, 192, 192), (1, 2, 2, 16, 16), (1, 34, 18, 48, 80)])
+def test_conv3x3_stride2_tcgen05_vs_oracle(cfg):
+    """FeaturePyramid's stride-2 convs on the tensor cores (2x2-cell formulation over a 5-D tensor map, k-steps without
+    weights skipped) against the fp32 oracle conv (TF SAME: even sizes pad bottom / right only), the FFMA2 kernel and an
+    fp64 evaluation; includes the 192-channel level (two launches over output-channel halves) and partial tiles."""
+    m = _m4d()
+    b, h, w, cin, cout = cfg
+    g = torch.Generator().manual_seed(cin * cout + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, 2))
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(cout, 2)
+    conv.assign(k, bias, "cuda")
+    assert conv.packed is not None
+    ffma = conv(cu(x), alpha=0.1, algo=1).clone()
+    tc = conv(cu(x), alpha=0.1, algo=2).clone()
+    assert tuple(tc.shape) == tuple(want.shape)
+    scale = float(want.abs().max())
+    np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * scale)
+    np.testing.assert_allclose(tc.cpu().numpy(), ffma.cpu().numpy(), rtol=1e-5, atol=1e-5 * scale)
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref64 = torch.nn.functional.conv2d(xp, k.double().permute(3, 2, 0, 1), bias.double(), stride=2)
+    ref64 = torch.nn.functional.leaky_relu(ref64, 0.1).permute(0, 2, 3, 1)
+    assert float((tc.cpu().double() - ref64).abs().max()) / scale < 4e-6
+    # odd sizes (TF pads both sides) stay on the FFMA2 kernel: auto falls back, forcing the tensor cores raises
+    xo = cu(torch.randn(1, 15, 20, cin, generator=g))
+    want_o = oracle.leaky_relu(oracle.conv2d_same(xo.cpu(), k, bias, 2))
+    np.testing.assert_allclose(conv(xo, alpha=0.1).cpu().numpy(), want_o.numpy(), rtol=1e-5, atol=1e-5 * float(want_o.abs().max()))
+    with pytest.raises(m.M4DError):
+        conv(xo, alpha=0.1, algo=2)
+
+
+def test_conv3x3_tcgen05_wide_output_split():
+    """cout = 192 (> 128 TMEM-friendly columns): two launches over halves of the output channels, stride 1 (128->192)."""
+    m = _m4d()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 12, 40, 128, generator=g)
+    k = torch.randn(3, 3, 128, 192, generator=g) * (2.0 / (9 * 128)) ** 0.5
+    bias = torch.randn(192, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, 1))
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(192, 1)
+    conv.assign(k, bias, "cuda")
+    tc = conv(cu(x), alpha=0.1, algo=2)
+    np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+
+
 def test_resize_and_prologue_epilogue_vs_oracle():
     m = _m4d()
     L = m._lib
