@@ -120,6 +120,13 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
  * out[b,y,x,(dy*(2r+1)+dx)*cuts + k] = leaky_0.1(mean_{j in group k} c1[b,y,x,j]*c2pad[b,y+dy-r,x+dx-r,j]) */
 int m4d_sncv_fwd(const float* c1, const float* c2, int b, int h, int w, int c, int cuts, int search_range,
                  float* out, int out_pix_stride, void* stream);
+/* variant: AUTO = the column-strip kernel where it applies (group width 16 / 24 / 32, cuts <= 4), else the (pixel, dy)
+ * kernel; PIXEL_DY forces the latter.  Both produce the same bits; tests cross-check them. */
+#define M4D_SNCV_AUTO 0
+#define M4D_SNCV_PIXEL_DY 1
+#define M4D_SNCV_COLUMN_STRIP 2 /* column-strip kernel whenever the shape allows, however few tiles */
+int m4d_sncv_fwd_ex(const float* c1, const float* c2, int b, int h, int w, int c, int cuts, int search_range,
+                    float* out, int out_pix_stride, int variant, void* stream);
 
 /* ---- L3: layer pieces (m4depth_network.py) ------------------------------------------------------*/
 /* tf.linalg.normalize per feature group, no epsilon (:180,185-186).  in/out [b,h,w,c] (may alias). */

@@ -327,6 +327,30 @@ def test_sncv_vs_oracle(shape):
     np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 80, 32, 2), (1, 37, 53, 16, 1), (1, 9, 33, 64, 2), (1, 30, 41, 96, 4),
+                                   (1, 15, 20, 128, 4), (1, 3, 5, 16, 1)])
+def test_sncv_column_strip_kernel_equals_pixel_dy_kernel(shape):
+    """The column-strip kernel (group widths 16 / 24 / 32, cuts <= 4; partial tiles, images smaller than a tile) is
+    bit-identical to the (pixel, dy) kernel, also when writing into a wider pixel stride."""
+    m = _m4d()
+    L = m._lib
+    b, h, w, c, cuts = shape
+    g = torch.Generator().manual_seed(h * w + c)
+    f = cu(torch.randn(b, h, w, c, generator=g))
+    f2 = cu(torch.randn(b, h, w, c, generator=g))
+    oc = 49 * cuts
+    outs = []
+    for variant in (2, 1, 0):
+        wide = torch.full((b, h, w, oc + 5), -7.0, device="cuda")
+        L.check(L.lib.m4d_sncv_fwd_ex(L.ptr(f), L.ptr(f2), b, h, w, c, cuts, 3, wide.data_ptr() + 8, oc + 5, variant, L.stream()))
+        outs.append(wide.cpu())
+    assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32))
+    assert torch.equal(outs[0].view(torch.int32), outs[2].view(torch.int32))
+    assert torch.all(outs[0][..., :2] == -7.0) and torch.all(outs[0][..., oc + 2:] == -7.0)
+    want = oracle.cost_volume(f.cpu(), f2.cpu(), 3, nbre_cuts=cuts)
+    np.testing.assert_allclose(outs[0][..., 2:oc + 2].numpy(), want.numpy(), rtol=1e-5, atol=1e-6)
+
+
 def test_backproject_op_vs_oracle():
     """General BackProject signature (S, F > 1), out-of-range and NaN coordinates, index grids bit-exact."""
     m = _m4d()

@@ -83,8 +83,11 @@ def sncv(b=8):
     for lvl, (h, w, c, cuts) in enumerate(LEVELS, 1):
         f = gn(torch.randn(b, h, w, c, device="cuda", generator=g), cuts)
         nbytes = 4 * h * w * (c + 49 * cuts) * b
-        med, mn = timeit(lambda: m.utils.cost_volume(f, f, 3, nbre_cuts=cuts))
-        print(f"sncv L{lvl} {h}x{w}x{c} b={b}: median {med:8.1f} us  min {mn:8.1f} us -> {nbytes / mn / 1e3:7.1f} GB/s ({nbytes / mn / 1e3 / PEAK * 100:5.1f}%)")
+        out = torch.empty(b, h, w, 49 * cuts, device="cuda")
+        L = m._lib
+        for variant, name in ((0, "auto"), (1, "pixel_dy")):
+            med, mn = timeit(lambda: L.check(L.lib.m4d_sncv_fwd_ex(L.ptr(f), L.ptr(f), b, h, w, c, cuts, 3, L.ptr(out), 49 * cuts, variant, L.stream())))
+            print(f"sncv L{lvl} {h}x{w}x{c} b={b} {name:8s}: median {med:8.1f} us  min {mn:8.1f} us -> {nbytes / mn / 1e3:7.1f} GB/s ({nbytes / mn / 1e3 / PEAK * 100:5.1f}%)")
 
 
 def conv(b=8):
