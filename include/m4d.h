@@ -161,12 +161,16 @@ int m4d_conv3x3_tc_fwd(const float* x, int x_pix_stride, const float* packed, co
                        int cin, int cout, float leaky_alpha, float* y, int y_pix_stride, void* stream);
 /* The same three calls with the stride explicit.  stride 2 = FeaturePyramid's down-sampling convs (m4depth_network.py:66-72)
  * as a 2x2-cell convolution on the tensor cores: needs even h and w (TF SAME then pads bottom / right only), cin % 16 == 0
- * and x_pix_stride == cin; odd sizes return M4D_ENOTSUP (callers fall back to m4d_conv3x3_nhwc).  cout up to 256 (even
- * beyond 128: two launches over halves of the output channels; the packed buffer holds both halves). */
+ * and x_pix_stride == cin; odd sizes return M4D_ENOTSUP (callers fall back to m4d_conv3x3_nhwc).  cout up to 256 (beyond
+ * 128 a pixel tile's output channels are split over 2 or 4 CTAs). */
 int64_t m4d_conv3x3_tc_packed_floats_s(int cin, int cout, int stride);
 int m4d_conv3x3_tc_pack_s(const float* kernel_hwio, int cin, int cout, int stride, float* packed, void* stream);
 int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
                          int cin, int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, void* stream);
+/* slices: 0 = let the library choose how many output-channel slices (1, 2 or 4 CTAs per pixel tile) a layer runs as -
+ * layers with fewer tiles than SMs are sliced to shorten the serial MMA chain; 1 / 2 / 4 force it (tests, tuning). */
+int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
+                          int cin, int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream);
 
 /* tf.compat.v1.image.resize_bilinear, align_corners=False, no half-pixel (:202-204); post_scale multiplies the
  * result (parallax is doubled after resizing).  in [b,ih,iw,c] -> out [b,oh,ow,c] with row stride. */

@@ -41,6 +41,8 @@ struct TcArgs {
   int cout_real;                    // channels actually stored
   int cin;                          // real input channels: k-steps of the last k-block that are all zero fill are skipped
   int tiles_x, tiles_y, ntiles;
+  int nslices, nitems;              // output-channel slices of width cout per tile; work items = ntiles * nslices
+  int ctot;                         // rows per weight plane in the packed buffer = all output channels rounded up to 16
   int nb;                           // weight-slab stages that fit in shared memory (3 at Cout = 128 ... 6)
   int nacc, nsets;                  // TMEM accumulators per tile (2 or 4) and accumulator sets (2 = epilogue overlaps the next tile)
   int tma_out;                      // epilogue through TMA stores (ys % 4 == 0 and y 16-byte aligned), else scalar stores
@@ -249,7 +251,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== A producer
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     int ka = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int tile = item / a.nslices;
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
       for (int kb = 0; kb < KB; ++kb, ++ka) {
@@ -271,7 +274,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int n0 = (item % a.nslices) * a.cout;                    // first output channel of this item's slice
       for (int kb = 0; kb < KB; ++kb) {
         const KbTaps tp = kb_taps<S2D>(a, kb);
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky)
@@ -280,11 +284,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             mbar_wait(b_empty + 8 * s, ((it / NB) & 1) ^ 1);
             if (elect_one()) {
               mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
-              tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, (kb * 9 + ky * 3 + kx) * 2 * a.cout);
+              const int row = (kb * 9 + ky * 3 + kx) * 2 * a.ctot + n0;   // the slice's rows of the hi plane; lo plane: + ctot
+              tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, row);
+              tma_load_2d(sB + s * b_stage_bytes + (uint32_t)a.cout * 128u, &tmap_w, b_full + 8 * s, 0, row + a.ctot);
             }
             __syncwarp();
           }
       }
+    }
   } else if (warp == 2) {
     // ===== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
@@ -302,7 +309,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // read from shared memory (128 B/clk), so one A pass less per k-step is 25-30 % of the layer.
     const uint32_t ncol = (uint32_t)a.cout;
     int ka = 0, it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
         const int set = ka & 1;
@@ -360,7 +367,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes
     const int t = threadIdx.x - 128;
     int ka = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x)
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int s = ka % A_STAGES;
         mbar_wait(a_full + 8 * s, (ka / A_STAGES) & 1);
@@ -389,7 +396,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t sbuf = sOut + (uint32_t)grp * OUT_SLOT;
     const int nchunks = (a.cout + 31) >> 5;
     int ka = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      const int tile = item / a.nslices;
+      const int n0 = (item - tile * a.nslices) * a.cout;
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
       float sum[2][32];
@@ -428,7 +437,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int nc = a.cout - c0 >= 32 ? 32 : 16;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nc) sum[ci][i] = leaky(sum[ci][i] + (c0 + i < a.cout_real ? __ldg(a.bias + c0 + i) : 0.f), a.alpha);
+          if (i < nc) sum[ci][i] = leaky(sum[ci][i] + (n0 + c0 + i < a.cout_real ? __ldg(a.bias + n0 + c0 + i) : 0.f), a.alpha);
         if (a.tma_out) {
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
           // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
@@ -446,14 +455,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (et == 0) {
             asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(&tmap_y), "r"(sbuf),
-                         "r"(c0), "r"(ox0), "r"(oy0), "r"(bi)
+                         "r"(n0 + c0), "r"(ox0), "r"(oy0), "r"(bi)
                          : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         } else if (valid) {                                         // pixel stride not a multiple of 16 bytes (the 5-channel output layer)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < nc && c0 + i < a.cout_real) yp[c0 + i] = sum[ci][i];
+            if (i < nc && n0 + c0 + i < a.cout_real) yp[n0 + c0 + i] = sum[ci][i];
         }
       }
     }
@@ -518,22 +527,40 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// Output channels beyond 128 (the 192-channel encoder level) run as two launches over halves of the channels.
-inline int tc_nsplit(int cout) { return cout <= 128 ? 1 : 2; }
 inline bool tc_shape_ok(int cin, int cout, int stride) {
-  if (cin < 1 || cout < 1 || cout > 256 || (cout > 128 && cout % 2 != 0)) return false;
+  if (cin < 1 || cout < 1 || cout > 256) return false;
   if (stride == 1) return true;
   return stride == 2 && cin % 16 == 0;          // the (px, c) range of a cell row splits into whole 32-channel k-blocks
 }
 inline int tc_cout_pad(int cout) { return (cout + 15) / 16 * 16; }
 inline int tc_kblocks(int cin, int stride) { return stride == 1 ? (cin + KC - 1) / KC : 2 * (2 * cin / KC); }
-inline int64_t tc_packed_half_floats(int cin, int cout_half, int stride) {
-  return (int64_t)tc_kblocks(cin, stride) * 9 * 2 * tc_cout_pad(cout_half) * KC;
+
+// Modelled clocks per k-step of one work item whose MMA N is n (shared-memory operand reads at 128 B/clk against the tensor
+// pipe's N/2 clocks per 128x N x8 MMA): three MMAs for n > 64, two (N = 2n and n) in the concatenated mode.
+inline int tc_kstep_clocks(int n) {
+  auto mma = [](int nn) { const int smem = 32 + nn / 4, tensor = nn / 2; return smem > tensor ? smem : tensor; };
+  return n > 64 ? 3 * mma(n) : mma(2 * n) + mma(n);
+}
+// Output-channel slices per tile.  One slice (N = all channels) does the least work per output, but a layer with fewer
+// tiles than SMs (pyramid levels 4-6) is a long serial MMA chain on a few SMs: slicing the channels over 2 or 4 CTAs
+// shortens the chain (N = 32: 88 clocks per k-step instead of 192 at N = 128) and fills the machine.  More than 128
+// channels (the 192-channel encoder level) always needs slices.  Picks the split with the fewest modelled clocks.
+inline int tc_pick_slices(int cout_pad, int64_t ntiles, int sms) {
+  int best = 0;
+  int64_t best_cost = 0;
+  for (int ns = 1; ns <= 4; ns *= 2) {
+    if (cout_pad % (16 * ns) != 0) continue;
+    const int n = cout_pad / ns;
+    if (n > 128 || (ns > 1 && n % 32 != 0)) continue;             // the epilogue's TMA stores are 32 channels wide
+    const int64_t waves = (ntiles * ns + sms - 1) / sms;
+    const int64_t cost = waves * (tc_kstep_clocks(n) + 12);       // + per-k-step issue / pipeline overhead of a work item
+    if (best == 0 || cost < best_cost) { best = ns; best_cost = cost; }
+  }
+  return best;
 }
 
-// one launch: output channels [0, cout) of `packed` into y (already offset by the caller)
 int tc_launch(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin, int cout,
-              int stride, float leaky_alpha, float* y, int y_pix_stride, cudaStream_t stream) {
+              int stride, float leaky_alpha, float* y, int y_pix_stride, int force_slices, cudaStream_t stream) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled is not available from this driver");
@@ -542,8 +569,15 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   const int kb = tc_kblocks(cin, stride);
   const int cout_real = cout;
   const bool tma_out = y_pix_stride % 4 == 0 && !(reinterpret_cast<uintptr_t>(y) & 15u);
-  cout = tc_cout_pad(cout);                    // from here on: the MMA N / packed row count
+  const int ctot = tc_cout_pad(cout);          // rows per weight plane of the packed buffer
   const int oh = stride == 1 ? h : h / 2, ow = stride == 1 ? w : w / 2;
+  const int64_t ntiles = (int64_t)((ow + TILE_W - 1) / TILE_W) * ((oh + TILE_H - 1) / TILE_H) * b;
+  M4D_REQUIRE(ntiles < (1ll << 28), "m4d_conv3x3_tc_fwd: too many tiles");
+  int nslices = force_slices > 0 ? force_slices : tc_pick_slices(ctot, ntiles, m4d_sm_count());
+  M4D_REQUIRE(nslices >= 1 && ctot % nslices == 0 && ctot / nslices <= 128 && (nslices == 1 || (ctot / nslices) % 32 == 0),
+              "m4d_conv3x3_tc_fwd: cannot slice %d output channels into %d (slices are multiples of 32 channels, at most 128)", cout_real,
+              nslices);
+  cout = ctot / nslices;                       // from here on: the MMA N = slice width
   CUtensorMap mx, mw, my;
   if (stride == 1) {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
@@ -571,9 +605,9 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     }
   }
   {
-    const cuuint64_t dims[2] = {KC, (cuuint64_t)kb * 9 * 2 * cout};
+    const cuuint64_t dims[2] = {KC, (cuuint64_t)kb * 9 * 2 * ctot};
     const cuuint64_t strides[1] = {KC * 4};
-    const cuuint32_t box[2] = {KC, (cuuint32_t)(2 * cout)};
+    const cuuint32_t box[2] = {KC, (cuuint32_t)cout};         // one plane's rows of a slice; two loads per stage
     const cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -604,9 +638,10 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.cin = stride == 1 ? cin : 4 * cin;
   a.tiles_x = (ow + TILE_W - 1) / TILE_W;
   a.tiles_y = (oh + TILE_H - 1) / TILE_H;
-  const int64_t ntiles = (int64_t)a.tiles_x * a.tiles_y * b;
-  M4D_REQUIRE(ntiles < (1ll << 30), "m4d_conv3x3_tc_fwd: too many tiles");
   a.ntiles = (int)ntiles;
+  a.nslices = nslices;
+  a.nitems = a.ntiles * nslices;
+  a.ctot = ctot;
   // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block; a set is [hi*hi | hi*lo | lo*hi] (Cout <= 64,
   // two MMAs per k-step) or [hi*hi | cross terms] (three MMAs per k-step).
   a.concat = cout <= 64 ? 1 : 0;
@@ -631,7 +666,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     }
     attr_set = true;
   }
-  const int grid = a.ntiles < m4d_sm_count() ? a.ntiles : m4d_sm_count();
+  const int grid = a.nitems < m4d_sm_count() ? a.nitems : m4d_sm_count();
   if (stride == 1) {
     if (a.concat) conv3x3_tc_kernel<false, true><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
     else conv3x3_tc_kernel<false, false><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
@@ -649,31 +684,25 @@ extern "C" {
 
 int64_t m4d_conv3x3_tc_packed_floats_s(int cin, int cout, int stride) {
   if (!tc_shape_ok(cin, cout, stride)) return 0;
-  const int ns = tc_nsplit(cout);
-  return ns * tc_packed_half_floats(cin, cout / ns, stride);
+  return (int64_t)tc_kblocks(cin, stride) * 9 * 2 * tc_cout_pad(cout) * KC;
 }
 
 int m4d_conv3x3_tc_pack_s(const float* kernel_hwio, int cin, int cout, int stride, float* packed, void* stream) {
   M4D_REQUIRE(kernel_hwio && packed, "m4d_conv3x3_tc_pack: null pointer");
   M4D_REQUIRE(tc_shape_ok(cin, cout, stride),
-              "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d stride=%d (cout <= 256, even beyond 128; stride 2 needs cin %% 16 == 0)",
-              cin, cout, stride);
+              "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d stride=%d (cout <= 256; stride 2 needs cin %% 16 == 0)", cin, cout, stride);
   const int kb = tc_kblocks(cin, stride);
-  const int ns = tc_nsplit(cout), ch = cout / ns;
-  const int cp = tc_cout_pad(ch);
+  const int cp = tc_cout_pad(cout);
   const int64_t n = (int64_t)kb * 9 * cp * KC;
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  for (int i = 0; i < ns; ++i) {
-    conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, i * ch, ch, cp, kb, stride == 1 ? 0 : cin,
-                                                                    stride == 1 ? 1 : 2 * cin / KC,
-                                                                    packed + i * tc_packed_half_floats(cin, ch, stride));
-    M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
-  }
+  conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, 0, cout, cp, kb, stride == 1 ? 0 : cin,
+                                                                  stride == 1 ? 1 : 2 * cin / KC, packed);
+  M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
   return M4D_OK;
 }
 
-int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
-                         int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
+int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                          int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream) {
   M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
   M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
   const bool s2_ok = stride != 2 || (h % 2 == 0 && w % 2 == 0 && x_pix_stride == cin);
@@ -683,13 +712,12 @@ int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, 
                   stride, h, w, x_pix_stride, y_pix_stride);
     return M4D_ENOTSUP;
   }
-  const int ns = tc_nsplit(cout), ch = cout / ns;
-  for (int i = 0; i < ns; ++i) {
-    const int rc = tc_launch(x, x_pix_stride, packed + i * tc_packed_half_floats(cin, ch, stride), bias + i * ch, b, h, w, cin, ch, stride,
-                             leaky_alpha, y + i * ch, y_pix_stride, (cudaStream_t)stream);
-    if (rc != M4D_OK) return rc;
-  }
-  return M4D_OK;
+  return tc_launch(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, leaky_alpha, y, y_pix_stride, slices, (cudaStream_t)stream);
+}
+
+int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                         int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
+  return m4d_conv3x3_tc_fwd_ex(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, leaky_alpha, y, y_pix_stride, 0, stream);
 }
 
 int64_t m4d_conv3x3_tc_packed_floats(int cin, int cout) { return m4d_conv3x3_tc_packed_floats_s(cin, cout, 1); }

@@ -91,7 +91,7 @@ class _Conv2D:
         s = self.strides
         return (b, -(-h // s), -(-w // s), self.filters)
 
-    def __call__(self, x, alpha=1.0, out=None, algo=0):
+    def __call__(self, x, alpha=1.0, out=None, algo=0, slices=0):
         if self.kernel is None:
             raise L.M4DError("conv layer has no weights: call load_weights() first")
         b, h, w, cin = x.shape
@@ -112,8 +112,8 @@ class _Conv2D:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            L.check(L.lib.m4d_conv3x3_tc_fwd_s(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
-                                               self.strides, float(alpha), L.ptr(out), ys, L.stream()))
+            L.check(L.lib.m4d_conv3x3_tc_fwd_ex(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
+                                                self.strides, float(alpha), L.ptr(out), ys, int(slices), L.stream()))
             if self.events is not None:
                 ev1.record()
                 self.events.append((ev0, ev1))

@@ -468,8 +468,42 @@ def test_conv3x3_stride2_tcgen05_vs_oracle(cfg):
         conv(xo, alpha=0.1, algo=2)
 
 
+@pytest.mark.parametrize("cfg", [(1, 6, 20, 470, 128, 1), (2, 12, 40, 238, 128, 1), (1, 12, 40, 128, 96, 1), (1, 9, 17, 96, 64, 1),
+                                 (1, 12, 40, 128, 128, 2), (1, 16, 8, 64, 192, 1)])
+def test_conv3x3_tcgen05_output_channel_slices(cfg):
+    """A pixel tile's output channels split over 1 / 2 / 4 CTAs (what the library does for layers with fewer tiles than
+    SMs): every legal split matches the oracle and the fp64 evaluation to the same tolerance as the unsplit kernel."""
+    m = _m4d()
+    b, h, w, cin, cout, stride = cfg
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, stride))
+    scale = float(want.abs().max())
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(cout, stride)
+    conv.assign(k, bias, "cuda")
+    xs = (cin + 3) // 4 * 4                       # 470 / 238 channels live in a 472 / 240-float pixel stride (refiner input)
+    wide = torch.zeros(b, h, w, xs)
+    wide[..., :cin] = x
+    xin = cu(wide)[..., :cin]
+    ran = 0
+    for slices in (0, 1, 2, 4):
+        cp = (cout + 15) // 16 * 16
+        legal = slices == 0 or (cp % slices == 0 and cp // slices <= 128 and (slices == 1 or (cp // slices) % 32 == 0))
+        if not legal:
+            with pytest.raises(m.M4DError):
+                conv(xin, alpha=0.1, algo=2, slices=slices)
+            continue
+        out = conv(xin, alpha=0.1, algo=2, slices=slices).clone()
+        np.testing.assert_allclose(out.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * scale)
+        ran += 1
+    assert ran >= 2
+
+
 def test_conv3x3_tcgen05_wide_output_split():
-    """cout = 192 (> 128 TMEM-friendly columns): two launches over halves of the output channels, stride 1 (128->192)."""
+    """cout = 192 (> 128 TMEM-friendly columns): output channels sliced over two CTAs per tile, stride 1 (128->192)."""
     m = _m4d()
     g = torch.Generator().manual_seed(5)
     x = torch.randn(1, 12, 40, 128, generator=g)
