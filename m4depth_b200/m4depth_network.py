@@ -438,6 +438,13 @@ class M4Depth:
         self._graphs.clear()
         self._seen.clear()
 
+    def load_checkpoint(self, source, which=None):
+        """Load a reference checkpoint: a TF tensor-bundle prefix (``.../cp-0071.ckpt``, what callbacks.py:119-129 saves)
+        or an archive such as the reference's ``pretrained_weights.zip`` with ``which`` in ("midair", "kitti").
+        Parsed without TensorFlow (m4depth_b200/checkpoint.py)."""
+        from .checkpoint import load_reference_weights
+        self.load_weights(load_reference_weights(source, which))
+
     def set_interp(self, mode):
         """Bilinear convention of the PSCV warp for every level (include/m4d.h M4D_INTERP_*)."""
         for lvl in self.d_estimator.levels:

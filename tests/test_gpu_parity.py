@@ -517,6 +517,32 @@ def test_conv3x3_tcgen05_wide_output_split():
     np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
 
 
+def test_model_loads_reference_format_checkpoint(tmp_path):
+    """Weights written in the reference's TF tensor-bundle format (object-graph key layout) load through
+    M4Depth.load_checkpoint and give the same depth, bit for bit, as the same weights passed as a dict."""
+    m = _m4d()
+    from m4depth_b200.checkpoint import save_reference_weights
+    nl, H, W = 3, 64, 96
+    wts = oracle.init_weights(nl, seed=4, bias_std=0.05, dn_random=True)
+    prefix = str(tmp_path / "cp-0001.ckpt")
+    save_reference_weights(prefix, wts)
+    g = torch.Generator().manual_seed(2)
+    cam = {"f": torch.tensor([[0.5 * W, 0.5 * H]]).cuda(), "c": torch.tensor([[0.5 * W, 0.5 * H]]).cuda()}
+    rot, trans = motion(g, 1)
+    frames = [torch.rand(1, H, W, 3, generator=g).cuda() for _ in range(2)]
+    outs = []
+    for loader in ("dict", "bundle"):
+        mod = m.M4Depth(nbre_levels=nl, use_cuda_graph=False)
+        if loader == "dict":
+            mod.load_weights(wts)
+        else:
+            mod.load_checkpoint(prefix)
+        for t, rgb in enumerate(frames):
+            out = mod([[{"RGB_im": rgb, "rot": rot.cuda(), "trans": trans.cuda(), "new_traj": [t == 0]}], cam])["depth"]
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
+
+
 def test_resize_and_prologue_epilogue_vs_oracle():
     m = _m4d()
     L = m._lib
