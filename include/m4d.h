@@ -53,6 +53,13 @@ uint64_t m4d_launch_count(void);
  * idx_dbg (nullable) int32 [B,H,W,S,F,4] receives the tap grid x0,x1,y0,y1 (-1 where outside). */
 int m4d_backproject_fwd(const float* input, const float* coords, const int32_t dim[6], float* out,
                         int32_t* idx_dbg, void* stream);
+/* Replaces BackProjectBackwardLauncher (backproject_op_gpu.h:20-22, kernel backproject_op_gpu.cu.cc:108-196) = TF op
+ * "BackProjectGrad" (backproject_op.cc:37-42), the gradient registered for BackProject (utils/dense_image_warp.py:46-52).
+ * grad [B,H,W,S,F,C] -> input_grad [B,H,W,F,C] (zeroed here, on the caller's stream, then scatter-added with
+ * floating-point atomics as in the reference: summation order not fixed) and coords_grad [B,H,W,S,F,2] (d/dx, d/dy; fully
+ * written, zero where the coordinate is outside the image or NaN; deterministic). */
+int m4d_backproject_bwd(const float* grad, const float* input, const float* coords, const int32_t dim[6],
+                        float* input_grad, float* coords_grad, void* stream);
 
 /* ---- L1: dense_image_warp (utils/dense_image_warp.py:195-268, BackProject branch :246-253) -------
  * image [b,h,w,c], flow [b,h,w,2] (row, col); query = grid + flow, clipped to the image. */

@@ -29,6 +29,7 @@ SIGNATURES = {
     "m4d_last_error_string": (C.c_char_p, []),
     "m4d_launch_count": (C.c_uint64, []),
     "m4d_backproject_fwd": (_i, [_p, _p, C.POINTER(C.c_int32), _p, _p, _p]),
+    "m4d_backproject_bwd": (_i, [_p, _p, _p, C.POINTER(C.c_int32), _p, _p, _p]),
     "m4d_dense_image_warp": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "m4d_get_rot_mat": (_i, [_p, _i, _i, _p, _p]),
     "m4d_prev_d2para": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _p, _p]),

@@ -30,6 +30,24 @@ def back_project(inputs, coords, return_index_grids=False):
     return (out, idx) if return_index_grids else out
 
 
+def back_project_grad(inputs, coords, grad):
+    """Gradient op of ``back_project`` (TF op BackProjectGrad, registered at utils/dense_image_warp.py:46-52):
+    (inputs [B,H,W,F,C], coords [B,H,W,S,F,2], grad [B,H,W,S,F,C]) -> (inputs_grad [B,H,W,F,C], coords_grad [B,H,W,S,F,2])."""
+    L.f32c(inputs, "inputs"), L.f32c(coords, "coords"), L.f32c(grad, "grad")
+    if inputs.dim() != 5 or coords.dim() != 6 or coords.shape[-1] != 2 or grad.dim() != 6:
+        raise L.M4DError("back_project_grad: inputs must be [B,H,W,F,C], coords [B,H,W,S,F,2], grad [B,H,W,S,F,C]")
+    B, H, W, Fd, Cc = inputs.shape
+    S = coords.shape[3]
+    if tuple(coords.shape[:3]) != (B, H, W) or coords.shape[4] != Fd or tuple(grad.shape) != (B, H, W, S, Fd, Cc):
+        raise L.M4DError("back_project_grad: shape mismatch")
+    inputs_grad = torch.empty_like(inputs)
+    coords_grad = torch.empty_like(coords)
+    dim = (C.c_int32 * 6)(B, H, W, S, Fd, Cc)
+    L.check(L.lib.m4d_backproject_bwd(L.ptr(grad), L.ptr(inputs), L.ptr(coords), dim, L.ptr(inputs_grad), L.ptr(coords_grad),
+                                      L.stream()))
+    return inputs_grad, coords_grad
+
+
 def dense_image_warp(image, flow, name='dense_image_warp'):
     """image [b,h,w,c], flow [b,h,w,2] (row, col) -> [b,h,w,c]; pixel (y,x) samples image at (y,x) + flow."""
     L.f32c(image, "image"), L.f32c(flow, "flow")

@@ -9,7 +9,7 @@ TF op, no autograd, no fused multiply-add across ops), of
 
 * ``utils/depth_operations.py:18-68,140-313``   (geometry, PSCV, SNCV)
 * ``utils/dense_image_warp.py:61-268``          (bilinear warp, both code paths)
-* ``cuda_backproject/backproject_op_gpu.cu.cc:19-79`` (BackProject forward)
+* ``cuda_backproject/backproject_op_gpu.cu.cc:19-79,108-196`` (BackProject forward and gradient)
 * ``m4depth_network.py:24-369``                 (DomainNormalization ... M4Depth.call)
 * ``metrics.py:1-64``
 
@@ -28,7 +28,7 @@ batched matmul summation order) is restated from TF 2.7's documented semantics a
 
 from .geometry import (get_rot_mat, get_coords_2d, parallax2depth, depth2parallax,
                        prev_d2para, pscv_query_points)
-from .warp import (interpolate_bilinear, back_project, dense_image_warp,
+from .warp import (interpolate_bilinear, back_project, back_project_grad, dense_image_warp,
                    back_project_index_grids)
 from .cost_volumes import get_parallax_sweeping_cv, cost_volume, tile_in_batch
 from .network import (conv2d_same, leaky_relu, resize_bilinear_legacy, resize_nearest,

@@ -97,6 +97,42 @@ def back_project(inputs, coords):
     return torch.where(inside.unsqueeze(-1), out, torch.zeros((), dtype=F32))
 
 
+def back_project_grad(inputs, coords, grad):
+    """BackProjectGrad (backproject_op_gpu.cu.cc:108-196; registered as the gradient of BackProject at
+    utils/dense_image_warp.py:46-52).  inputs [B,H,W,F,C], coords [B,H,W,S,F,2] (x,y), grad [B,H,W,S,F,C]
+    -> (inputs_grad [B,H,W,F,C], coords_grad [B,H,W,S,F,2]).
+
+    inputs_grad: grad * w_ij scatter-added onto the four taps (:178-181; the reference's atomicAdd order is not fixed,
+    here index_add in sample order).  coords_grad (:183-184, summed over channels in order):
+        d/dx = sum_c g * ((1-dy)*(I01 - I00) + dy*(I11 - I10)),   d/dy = sum_c g * ((1-dx)*(I10 - I00) + dx*(I11 - I01));
+    both zero where the coordinate is outside [0,W-1]x[0,H-1] or NaN (memsets at :209-210 + guard at :130)."""
+    B, H, W, Fd, C = inputs.shape
+    S = coords.shape[3]
+    x0, x1, y0, y1, inside = back_project_index_grids(coords, H, W)
+    x = torch.where(inside, coords[..., 0], torch.zeros((), dtype=F32))
+    y = torch.where(inside, coords[..., 1], torch.zeros((), dtype=F32))
+    x0c, x1c = x0.clamp(min=0).to(torch.int64), x1.clamp(min=0).to(torch.int64)
+    y0c, y1c = y0.clamp(min=0).to(torch.int64), y1.clamp(min=0).to(torch.int64)
+    dx = (x - x0c.to(F32)).unsqueeze(-1)
+    dy = (y - y0c.to(F32)).unsqueeze(-1)
+    wx0, wx1, wy0, wy1 = 1 - dx, dx, 1 - dy, dy
+    flat = inputs.reshape(B * H * W * Fd, C)
+    bidx = torch.arange(B, dtype=torch.int64).view(B, 1, 1, 1, 1)
+    fidx = torch.arange(Fd, dtype=torch.int64).view(1, 1, 1, 1, Fd)
+    m = inside.unsqueeze(-1).to(F32)
+    g = grad * m
+    igrad = torch.zeros_like(flat)
+    taps = {}
+    for name, yy, xx, wgt in (("00", y0c, x0c, wy0 * wx0), ("01", y0c, x1c, wy0 * wx1),
+                              ("10", y1c, x0c, wy1 * wx0), ("11", y1c, x1c, wy1 * wx1)):
+        lin = (((bidx * H + yy) * W + xx) * Fd + fidx).reshape(-1)
+        taps[name] = flat[lin].reshape(B, H, W, S, Fd, C)
+        igrad.index_add_(0, lin, (g * wgt).reshape(-1, C))
+    gx = (g * (wy0 * (taps["01"] - taps["00"]) + wy1 * (taps["11"] - taps["10"]))).sum(-1)
+    gy = (g * (wx0 * (taps["10"] - taps["00"]) + wx1 * (taps["11"] - taps["01"]))).sum(-1)
+    return igrad.reshape(B, H, W, Fd, C), torch.stack((gx, gy), dim=-1)
+
+
 def dense_image_warp(image, flow, use_cuda_backproject=False):
     """image [b,h,w,c], flow [b,h,w,2] (row, col) -> [b,h,w,c]; query = grid + flow (:244).
 

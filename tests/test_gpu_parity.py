@@ -372,6 +372,38 @@ def test_backproject_op_vs_oracle():
                                oracle.back_project(inp8, coords).numpy(), rtol=0, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(2, 7, 9, 3, 2, 5), (1, 12, 16, 9, 1, 32), (2, 6, 5, 1, 1, 33), (1, 4, 4, 2, 3, 8)])
+def test_backproject_grad_vs_oracle(shape):
+    """BackProjectGrad (the gradient TF registers for BackProject): scatter of grad*w onto the taps and the coordinate
+    gradient, general (S, F), channel counts with and without the float4 path, coordinates outside the image, NaN and
+    integral coordinates.  inputs_grad is a floating-point scatter-add (order not fixed, as in the reference): 1e-5."""
+    m = _m4d()
+    B, H, W, S, Fd, C = shape
+    g = torch.Generator().manual_seed(B * H + C)
+    inp = torch.randn(B, H, W, Fd, C, generator=g)
+    coords = torch.rand(B, H, W, S, Fd, 2, generator=g) * torch.tensor([W + 2.0, H + 2.0]) - 1.0
+    coords[0, 0, 0, 0, 0, 0] = float("nan")
+    coords[0, 1, 1, 0, 0] = torch.tensor([3.0, 2.0])            # integral coordinate: ceil == floor, both taps coincide
+    coords[-1, 2, 2, -1, -1] = torch.tensor([W - 1.0, H - 1.0])
+    grad = torch.randn(B, H, W, S, Fd, C, generator=g)
+    want_i, want_c = oracle.back_project_grad(inp, coords, grad)
+    d_inp, d_coords, d_grad = cu(inp), cu(coords), cu(grad)
+    got_i, got_c = m.utils.back_project_grad(d_inp, d_coords, d_grad)
+    scale = float(want_i.abs().max())
+    np.testing.assert_allclose(got_i.cpu().numpy(), want_i.numpy(), rtol=1e-5, atol=1e-5 * scale)
+    np.testing.assert_allclose(got_c.cpu().numpy(), want_c.numpy(), rtol=1e-4, atol=1e-5 * float(want_c.abs().max()))
+    # coords_grad is deterministic and fully written (zeros outside), inputs_grad starts from zero on every call
+    poison_i, poison_c = torch.full_like(got_i, 9.0), torch.full_like(got_c, 9.0)
+    L = m._lib
+    import ctypes
+    dim = (ctypes.c_int32 * 6)(B, H, W, S, Fd, C)
+    L.check(L.lib.m4d_backproject_bwd(L.ptr(d_grad), L.ptr(d_inp), L.ptr(d_coords), dim, L.ptr(poison_i), L.ptr(poison_c), L.stream()))
+    assert torch.equal(poison_c, got_c)
+    np.testing.assert_allclose(poison_i.cpu().numpy(), got_i.cpu().numpy(), rtol=1e-5, atol=1e-5 * scale)
+    outside = ~((coords[..., 0] >= 0) & (coords[..., 1] >= 0) & (coords[..., 0] <= W - 1) & (coords[..., 1] <= H - 1))
+    assert torch.all(got_c.cpu()[outside] == 0)
+
+
 @pytest.mark.parametrize("cfg", [(2, 9, 13, 3, 16, 1), (1, 16, 16, 16, 16, 2), (2, 15, 20, 24, 40, 2), (1, 8, 12, 122, 128, 1),
                                  (1, 6, 20, 470, 128, 1), (2, 10, 7, 16, 5, 1), (1, 33, 47, 64, 96, 2), (1, 12, 40, 238, 128, 1)])
 def test_conv3x3_vs_oracle(cfg):

@@ -114,3 +114,36 @@ def test_oracle_sqrt_is_correctly_rounded():
     x = torch.exp(torch.rand(1 << 18, generator=g) * 40 - 20)
     want = torch.from_numpy(np.sqrt(x.numpy().astype(np.float64)).astype(np.float32))
     assert torch.equal(sqrt(x), want)
+
+
+def test_back_project_grad_restatement_matches_autograd_of_the_forward():
+    """The oracle's BackProjectGrad (restated from backproject_op_gpu.cu.cc:108-196) equals the autograd gradient of the
+    oracle's BackProject forward (fp64, away from integer coordinates where the bilinear kernel is not differentiable)."""
+    g = torch.Generator().manual_seed(3)
+    B, H, W, S, Fd, C = 2, 6, 7, 3, 2, 5
+    inp = torch.randn(B, H, W, Fd, C, generator=g)
+    frac = 0.1 + 0.8 * torch.rand(B, H, W, S, Fd, 2, generator=g)
+    base = torch.stack((torch.randint(-1, W, (B, H, W, S, Fd), generator=g), torch.randint(-1, H, (B, H, W, S, Fd), generator=g)), -1)
+    coords = (base + frac).to(torch.float32)               # some samples fall outside the image: zero gradient there
+    grad = torch.randn(B, H, W, S, Fd, C, generator=g)
+    ig, cg = oracle.back_project_grad(inp, coords, grad)
+
+    def fwd64(i, c):
+        x, y = c[..., 0], c[..., 1]
+        inside = (x >= 0) & (y >= 0) & (x <= W - 1) & (y <= H - 1)
+        x0, y0 = torch.floor(x).clamp(0, W - 1).long(), torch.floor(y).clamp(0, H - 1).long()
+        x1, y1 = torch.ceil(x).clamp(0, W - 1).long(), torch.ceil(y).clamp(0, H - 1).long()
+        dx, dy = (x - x0).unsqueeze(-1), (y - y0).unsqueeze(-1)
+        bi = torch.arange(B).view(B, 1, 1, 1, 1).expand_as(x0)
+        fi = torch.arange(Fd).view(1, 1, 1, 1, Fd).expand_as(x0)
+        tap = lambda yy, xx: i[bi, yy, xx, fi]
+        out = tap(y0, x0) * (1 - dy) * (1 - dx) + tap(y0, x1) * (1 - dy) * dx + tap(y1, x0) * dy * (1 - dx) + tap(y1, x1) * dy * dx
+        return out * inside.unsqueeze(-1)
+
+    i64 = inp.double().requires_grad_(True)
+    c64 = coords.double().requires_grad_(True)
+    (fwd64(i64, c64) * grad.double()).sum().backward()
+    np.testing.assert_allclose(ig.numpy(), i64.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(cg.numpy(), c64.grad.numpy(), rtol=1e-4, atol=1e-4)
+    # and the forward used for the autograd check is the oracle's forward
+    np.testing.assert_allclose(oracle.back_project(inp, coords).numpy(), fwd64(inp.double(), coords.double()).detach().numpy(), atol=1e-5)
