@@ -178,6 +178,18 @@ int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, 
  * layers with fewer tiles than SMs are sliced to shorten the serial MMA chain; 1 / 2 / 4 force it (tests, tuning). */
 int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
                           int cin, int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream);
+/* Precision mode of the tensor-core path, chosen at pack time (the packed layouts differ) and passed again to the forward:
+ *   3XTF32  operands split into TF32 hi + lo, kind::tf32 MMAs (the calls above)
+ *   3XFP16  operands scaled by a power of two (per layer for the weights, per pixel tile and 32-channel block for the
+ *           activations, from the data) and split into fp16 h1 + 2^-11 h2, kind::f16 MMAs at twice the TF32 rate; the same
+ *           three products hi*hi + hi*lo + lo*hi with fp32 accumulation, i.e. the same ~2^-22 relative error class. */
+#define M4D_CONV_PREC_3XTF32 0
+#define M4D_CONV_PREC_3XFP16 1
+int64_t m4d_conv3x3_tc_packed_floats_p(int cin, int cout, int stride, int prec);
+int m4d_conv3x3_tc_pack_p(const float* kernel_hwio, int cin, int cout, int stride, int prec, float* packed, void* stream);
+int m4d_conv3x3_tc_fwd_p(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
+                         int cin, int cout, int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int slices,
+                         void* stream);
 
 /* tf.compat.v1.image.resize_bilinear, align_corners=False, no half-pixel (:202-204); post_scale multiplies the
  * result (parallax is doubled after resizing).  in [b,ih,iw,c] -> out [b,oh,ow,c] with row stride. */

@@ -51,6 +51,9 @@ SIGNATURES = {
     "m4d_conv3x3_tc_pack_s": (_i, [_p, _i, _i, _i, _p, _p]),
     "m4d_conv3x3_tc_fwd_s": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]),
     "m4d_conv3x3_tc_fwd_ex": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p]),
+    "m4d_conv3x3_tc_packed_floats_p": (C.c_int64, [_i, _i, _i, _i]),
+    "m4d_conv3x3_tc_pack_p": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "m4d_conv3x3_tc_fwd_p": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p]),
     "m4d_resize_bilinear_legacy": (_i, [_p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]),
     "m4d_resize_nearest": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
     "m4d_level_prologue": (_i, [_p, _p, _p, _i, _i, _p, _p, _i, _p, _p, _p, _i, _i, _i,

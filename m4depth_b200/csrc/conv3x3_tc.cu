@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace {
@@ -30,6 +31,10 @@ constexpr int KC = 32;                                         // channels per k
 constexpr int A_BYTES = HALO_W * HALO_H * KC * 4;              // 23040: one halo plane as landed by TMA
 constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;         // 23552
 constexpr int A_STAGES = 2;
+// 3xFP16 mode: the fp32 halo lands in the first A_SLOT bytes of a stage, its two fp16 planes (64-byte rows) follow
+constexpr int AH_PLANE = (HALO_W * HALO_H * KC * 2 + 1023) / 1024 * 1024;   // 12288
+constexpr int A_STAGE_BYTES_F32 = 2 * A_SLOT;
+constexpr int A_STAGE_BYTES_F16 = A_SLOT + 2 * AH_PLANE;
 constexpr int MAX_B_STAGES = 6;
 constexpr int OUT_SLOT = 128 * 128;                            // one [128 px][32 ch] fp32 staging tile
 constexpr int NTHREADS = 512;
@@ -49,6 +54,7 @@ struct TcArgs {
   int concat;                       // Cout <= 64: hi*hi and hi*lo in ONE MMA of N = 2*Cout over the adjacent [hi|lo] weight planes
   int s2d_c;                        // 0: stride 1.  C > 0: stride-2 conv over C input channels as a 2x2-cell conv (see below)
   int s2d_chunks;                   // 32-channel chunks of one input row pair's (px, c) range = 2C / 32
+  const float* w_scale;             // 3xFP16 mode: 1 / (power-of-two scale the packed weights were multiplied by), device scalar
   float alpha;
 };
 
@@ -68,19 +74,20 @@ struct KbTaps {
   __device__ __forceinline__ int nk(int kx) const { return kx == 2 ? nks2 : nks; }
   __device__ __forceinline__ int kx_hi() const { return nks2 > 0 ? 2 : 1; }
 };
-template <bool S2D>
+// KS = channels per MMA k-step: 8 (kind::tf32) or 16 (kind::f16)
+template <bool S2D, int KS>
 __device__ __forceinline__ KbTaps kb_taps(const TcArgs& a, int kb) {
   KbTaps t;
   if (!S2D) {
     const int rem = a.cin - kb * KC;
-    t.nks = t.nks2 = rem >= KC ? KC / 8 : (rem + 7) >> 3;          // 16-channel inputs: 2 of the 4 k-steps are zero fill
+    t.nks = t.nks2 = rem >= KC ? KC / KS : (rem + KS - 1) / KS;    // 16-channel inputs: half of the k-steps are zero fill
     t.ky_lo = 0; t.ky_hi = 2; t.kx_lo = 0;
   } else {
     const int py = kb / a.s2d_chunks;
     const int ch0 = (kb - py * a.s2d_chunks) * KC;                 // first (px, c) index of this k-block; px = index / C
     const int left = a.s2d_c - ch0;                                // channels of this k-block that belong to px = 0
-    t.nks = KC / 8;
-    t.nks2 = left <= 0 ? 0 : (left >= KC ? KC / 8 : (left + 7) >> 3);
+    t.nks = KC / KS;
+    t.nks2 = left <= 0 ? 0 : (left >= KC ? KC / KS : (left + KS - 1) / KS);
     t.ky_lo = 1; t.ky_hi = py ? 1 : 2; t.kx_lo = 1;
   }
   return t;
@@ -147,10 +154,22 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address and the byte
 // stride between 8-row groups in 16-byte units, LBO = 1 (unused for swizzled K-major), version 1, layout type 2.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+// the same for SWIZZLE_64B (64-byte rows: 32 fp16 channels per pixel / per output channel), layout type 4
+__device__ __forceinline__ uint64_t umma_desc64(uint32_t saddr, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (4ull << 61);
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -198,21 +217,32 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 // All rings run across tile boundaries, so the loads and the split of tile i+1 and the whole epilogue of tile i overlap
 // with the MMAs (measured before this structure: 30 % of a 128-column tile was un-overlapped prologue + epilogue,
 // profiles/r1f_conv_tc_tile_phases.md).
-template <bool S2D, bool CONCAT>
+// HALF = 3xFP16 instead of 3xTF32 (same hi*hi + hi*lo + lo*hi scheme, same 2^-22 class of error, twice the tensor-core rate
+// and half the operand bytes): every operand is x * s = h1 + 2^-11 * h2 with fp16 h1 = rn(x * s), h2 = rn((x * s - h1) * 2^11)
+// and a power-of-two scale s that puts the largest magnitude just below 2^15 - per layer for the weights (at pack time),
+// per (pixel tile, k-block) for the activations (by the splitter warps, from the landed halo) - so fp16's narrow exponent
+// range costs nothing: the epilogue warps multiply each k-block's accumulators by 1 / (s_x * s_w) (and the cross terms by
+// 2^-11) while adding them into their fp32 register sums.  fp16 x fp16 products are exact in the fp32 accumulator.
+template <bool S2D, bool CONCAT, bool HALF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_y, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024-byte alignment
-  const uint32_t b_stage_bytes = 2u * (uint32_t)a.cout * 128u;                // hi + lo planes of [Cout][32]
-  const uint32_t sA = smem0;                                                  // [A_STAGES][hi, lo][A_SLOT]
-  const uint32_t sOut = sA + A_STAGES * 2 * A_SLOT;                           // [2][128 px][32 ch] staging for the TMA stores
+  constexpr int KS = HALF ? 16 : 8;                                           // channels per MMA k-step
+  constexpr uint32_t ROWB = HALF ? 64u : 128u;                                // bytes per operand row (32 channels)
+  constexpr uint32_t A_STAGE = HALF ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;               // swizzled tiles need 1024-byte alignment
+  const uint32_t b_stage_bytes = 2u * (uint32_t)a.cout * ROWB;                // hi + lo planes of [Cout][32]
+  const uint32_t sA = smem0;                                                  // [A_STAGES][A_STAGE]
+  const uint32_t sOut = sA + A_STAGES * A_STAGE;                              // [2][128 px][32 ch] staging for the TMA stores
   const uint32_t sB = sOut + 2 * OUT_SLOT;                                    // [nb][b_stage_bytes]
   const uint32_t sBar = sB + (uint32_t)a.nb * b_stage_bytes;
   const uint32_t a_full = sBar, a_ready = sBar + 8 * A_STAGES, a_empty = sBar + 16 * A_STAGES;
   const uint32_t b_full = sBar + 24 * A_STAGES, b_empty = b_full + 8 * MAX_B_STAGES;
   const uint32_t acc_full = b_empty + 8 * MAX_B_STAGES, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t s_max = tmem_slot + 16;                                      // [A_STAGES] uint: max |x| bits of the landed halo
+  const uint32_t s_scale = s_max + 16;                                        // [4] float: 1 / (s_x * s_w) of k-block ka & 3
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = a.kblocks, NB = a.nb;
@@ -233,6 +263,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(acc_empty + 8 * s, 8);          // one lane of each of the 8 epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int i = 0; i < A_STAGES; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
   }
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
@@ -261,10 +292,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (elect_one()) {
           mbar_expect_tx(a_full + 8 * s, A_BYTES);
           if (!S2D) {
-            tma_load_4d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
+            tma_load_4d(sA + s * A_STAGE, &tmap_x, a_full + 8 * s, kb * KC, ox0 - 1, oy0 - 1, bi);
           } else {
             const int py = kb / a.s2d_chunks;
-            tma_load_5d(sA + s * 2 * A_SLOT, &tmap_x, a_full + 8 * s, (kb - py * a.s2d_chunks) * KC, ox0 - 1, py, oy0 - 1, bi);
+            tma_load_5d(sA + s * A_STAGE, &tmap_x, a_full + 8 * s, (kb - py * a.s2d_chunks) * KC, ox0 - 1, py, oy0 - 1, bi);
           }
         }
         __syncwarp();
@@ -277,7 +308,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int n0 = (item % a.nslices) * a.cout;                    // first output channel of this item's slice
       for (int kb = 0; kb < KB; ++kb) {
-        const KbTaps tp = kb_taps<S2D>(a, kb);
+        const KbTaps tp = kb_taps<S2D, KS>(a, kb);
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky)
           for (int kx = tp.kx_lo; kx <= tp.kx_hi(); ++kx, ++it) {
             const int s = it % NB;
@@ -286,7 +317,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
               const int row = (kb * 9 + ky * 3 + kx) * 2 * a.ctot + n0;   // the slice's rows of the hi plane; lo plane: + ctot
               tma_load_2d(sB + s * b_stage_bytes, &tmap_w, b_full + 8 * s, 0, row);
-              tma_load_2d(sB + s * b_stage_bytes + (uint32_t)a.cout * 128u, &tmap_w, b_full + 8 * s, 0, row + a.ctot);
+              tma_load_2d(sB + s * b_stage_bytes + (uint32_t)a.cout * ROWB, &tmap_w, b_full + 8 * s, 0, row + a.ctot);
             }
             __syncwarp();
           }
@@ -295,9 +326,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   } else if (warp == 2) {
     // ===== MMA issuer
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.cout >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*Cout
-    const uint32_t lo_off16 = ((uint32_t)a.cout * 128u) >> 4;
+    // (operand format field: 2 = TF32, 0 = F16)
+    const uint32_t fmt = HALF ? 0u : ((2u << 7) | (2u << 10));
+    const uint32_t idesc = (1u << 4) | fmt | ((uint32_t)(a.cout >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | fmt | ((uint32_t)(a.cout >> 2) << 17) | ((128u >> 4) << 24);   // N = 2*Cout
+    const uint32_t lo_off16 = ((uint32_t)a.cout * ROWB) >> 4;
     // The tensor core adds every K=8 partial product to the fp32 accumulator with TRUNCATION, so the error is biased and
     // grows with the number of additions made at full magnitude (one accumulator per tile: 1e-5 of the scale at cin = 128,
     // and the bias survives into the depth maps).  Two measures keep the kernel in the FFMA class: every k-block starts
@@ -319,9 +352,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int sa = ka % A_STAGES;
         mbar_wait(a_ready + 8 * sa, (ka / A_STAGES) & 1);
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
-        const uint64_t dA_hi = umma_desc(sA + sa * 2 * A_SLOT, HALO_W * 128);
-        const uint64_t dA_lo = umma_desc(sA + sa * 2 * A_SLOT + A_SLOT, HALO_W * 128);
-        const KbTaps tp = kb_taps<S2D>(a, kb);
+        const uint64_t dA_hi = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT, HALO_W * 64) : umma_desc(sA + sa * A_STAGE, HALO_W * 128);
+        const uint64_t dA_lo = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT + AH_PLANE, HALO_W * 64)
+                                    : umma_desc(sA + sa * A_STAGE + A_SLOT, HALO_W * 128);
+        const KbTaps tp = kb_taps<S2D, KS>(a, kb);
         const int kx_hi = tp.kx_hi();
 #pragma unroll 1
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky) {
@@ -334,16 +368,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             ++it;
             tc_fence_after();
             if (elect_one()) {
-              const uint64_t dB_hi = umma_desc(sB + sb * b_stage_bytes, 1024);
-              const uint32_t tap16 = (uint32_t)((ky * HALO_W + kx) * 128) >> 4;
+              const uint64_t dB_hi = HALF ? umma_desc64(sB + sb * b_stage_bytes, 512) : umma_desc(sB + sb * b_stage_bytes, 1024);
+              const uint32_t tap16 = ((uint32_t)(ky * HALO_W + kx) * ROWB) >> 4;
               const uint32_t later = (ky > tp.ky_lo || kx > (S2D ? 1 : 0)) ? 1u : 0u;     // past the first tap of the k-block
 #pragma unroll
-              for (int ks = 0; ks < KC / 8; ++ks) {
+              for (int ks = 0; ks < KC / KS; ++ks) {              // a k-step is 32 bytes of a row in either format
                 if (ks >= nk) break;
                 const uint64_t a_hi = dA_hi + tap16 + ks * 2, a_lo = dA_lo + tap16 + ks * 2;
                 const uint64_t b_hi = dB_hi + ks * 2, b_lo = dB_hi + lo_off16 + ks * 2;
                 const uint32_t acc = ks > 0 ? 1u : later;
-                if (CONCAT) {
+                if (HALF) {
+                  if (CONCAT) {
+                    tc_mma_f16(d_set, a_hi, b_hi, idesc2, acc);
+                    tc_mma_f16(d_corr, a_lo, b_hi, idesc, acc);
+                  } else {
+                    tc_mma_f16(d_set, a_hi, b_hi, idesc, acc);
+                    tc_mma_f16(d_corr, a_lo, b_hi, idesc, acc);
+                    tc_mma_f16(d_corr, a_hi, b_lo, idesc, 1u);
+                  }
+                } else if (CONCAT) {
                   tc_mma_tf32(d_set, a_hi, b_hi, idesc2, acc);
                   tc_mma_tf32(d_corr, a_lo, b_hi, idesc, acc);
                 } else {
@@ -371,17 +414,79 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int s = ka % A_STAGES;
         mbar_wait(a_full + 8 * s, (ka / A_STAGES) & 1);
-        const uint32_t hi_p = sA + s * 2 * A_SLOT, lo_p = hi_p + A_SLOT;
+        const uint32_t hi_p = sA + s * A_STAGE, lo_p = hi_p + A_SLOT;
+        if (!HALF) {
 #pragma unroll 4
-        for (int i = t; i < A_BYTES / 16; i += 128) {
-          const uint4 v = lds128(hi_p + i * 16);
-          uint4 hi, lo;
-          split_tf32(v.x, hi.x, lo.x);
-          split_tf32(v.y, hi.y, lo.y);
-          split_tf32(v.z, hi.z, lo.z);
-          split_tf32(v.w, hi.w, lo.w);
-          sts128(hi_p + i * 16, hi);
-          sts128(lo_p + i * 16, lo);
+          for (int i = t; i < A_BYTES / 16; i += 128) {
+            const uint4 v = lds128(hi_p + i * 16);
+            uint4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x);
+            split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z);
+            split_tf32(v.w, hi.w, lo.w);
+            sts128(hi_p + i * 16, hi);
+            sts128(lo_p + i * 16, lo);
+          }
+        } else {
+          // a unit = 8 channels of one halo pixel: two 16-byte chunks of the landed fp32 row (SWIZZLE_128B: chunk c of
+          // row r lives at c ^ (r & 7)) -> one 16-byte chunk of each fp16 plane (SWIZZLE_64B: chunk j of row r at
+          // j ^ ((r >> 1) & 3); both follow from the absolute shared-memory address, the planes are 1024-byte aligned)
+          constexpr int NU = HALO_W * HALO_H * 4, UPT = (NU + 127) / 128;
+          uint4 va[UPT], vb[UPT];
+          uint32_t mx = 0u;
+#pragma unroll
+          for (int u = 0; u < UPT; ++u) {
+            const int idx = t + u * 128;
+            if (idx < NU) {
+              const int px = idx >> 2, j = idx & 3;
+              const uint32_t row = hi_p + (uint32_t)px * 128u;
+              va[u] = lds128(row + (uint32_t)(((2 * j) ^ (px & 7)) * 16));
+              vb[u] = lds128(row + (uint32_t)(((2 * j + 1) ^ (px & 7)) * 16));
+              mx = max(mx, max(max(va[u].x & 0x7FFFFFFFu, va[u].y & 0x7FFFFFFFu), max(va[u].z & 0x7FFFFFFFu, va[u].w & 0x7FFFFFFFu)));
+              mx = max(mx, max(max(vb[u].x & 0x7FFFFFFFu, vb[u].y & 0x7FFFFFFFu), max(vb[u].z & 0x7FFFFFFFu, vb[u].w & 0x7FFFFFFFu)));
+            }
+          }
+          // largest magnitude of the k-block's halo (compared as the bits of |x|: monotonic for finite values)
+#pragma unroll
+          for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+          if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(mx) : "memory");
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+          uint32_t mbits;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(s_max + 4 * s) : "memory");
+          // s_x = 2^(14 - E) with E the exponent of the maximum (so max * s_x is in [2^14, 2^15)); exponents are clamped so that
+          // s_x and 1 / s_x are normal floats (all-zero / denormal tiles: any scale gives zeros)
+          int E = (int)(mbits >> 23) - 127;
+          E = E < -100 ? -100 : (E > 100 ? 100 : E);
+          const float sx = __uint_as_float((uint32_t)(127 + 14 - E) << 23);
+          asm volatile("bar.sync 3, 128;" ::: "memory");                 // everyone has read the maximum
+          if (t == 0) {
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(0u) : "memory");
+            const float inv = __uint_as_float((uint32_t)(127 - 14 + E) << 23) * __ldg(a.w_scale);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_scale + 4 * (ka & 3)), "f"(inv) : "memory");
+          }
+          const uint32_t h1_p = hi_p + A_SLOT, h2_p = h1_p + AH_PLANE;
+#pragma unroll
+          for (int u = 0; u < UPT; ++u) {
+            const int idx = t + u * 128;
+            if (idx < NU) {
+              const int px = idx >> 2, j = idx & 3;
+              const float x[8] = {__uint_as_float(va[u].x) * sx, __uint_as_float(va[u].y) * sx, __uint_as_float(va[u].z) * sx,
+                                  __uint_as_float(va[u].w) * sx, __uint_as_float(vb[u].x) * sx, __uint_as_float(vb[u].y) * sx,
+                                  __uint_as_float(vb[u].z) * sx, __uint_as_float(vb[u].w) * sx};
+              uint32_t h1[4], h2[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn((x[2 * i] - hf.x) * 2048.f, (x[2 * i + 1] - hf.y) * 2048.f);
+                h1[i] = *reinterpret_cast<const uint32_t*>(&h);
+                h2[i] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              const uint32_t off = (uint32_t)px * 64u + (uint32_t)((j ^ ((px >> 1) & 3)) * 16);
+              sts128(h1_p + off, make_uint4(h1[0], h1[1], h1[2], h1[3]));
+              sts128(h2_p + off, make_uint4(h2[0], h2[1], h2[2], h2[3]));
+            }
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
         mbar_arrive(a_ready + 8 * s);
@@ -407,19 +512,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         mbar_wait(acc_full + 8 * set, (ka >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
+        float inv_main = 1.f;                                       // 3xFP16: 1 / (s_x * s_w) of this k-block, cross terms * 2^-11
+        if (HALF) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_main) : "r"(s_scale + 4 * (ka & 3)) : "memory");
+        const float inv_cross = inv_main * (1.0f / 2048.0f);
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int c0 = (grp + 2 * ci) * 32;
           if (c0 < a.cout) {
             const int nc = a.cout - c0 >= 32 ? 32 : 16;
-            for (int jj = 0; jj < a.nacc; ++jj) {                   // (main0 [+ main1 + main2]) + cross terms
+            for (int jj = 0; jj < a.nacc; ++jj) {                   // hi*hi, then the cross-term accumulator(s)
               uint32_t v[32];
               if (nc == 32) tc_ld32(trow + jj * a.cout + c0, v);
               else tc_ld16(trow + jj * a.cout + c0, v);
               tc_ld_wait();
+              const float sc = jj == 0 ? inv_main : inv_cross;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nc) sum[ci][i] = (kb == 0 && jj == 0) ? __uint_as_float(v[i]) : sum[ci][i] + __uint_as_float(v[i]);
+                if (i < nc) {
+                  if (HALF) sum[ci][i] = (kb == 0 && jj == 0) ? __uint_as_float(v[i]) * sc : fmaf(__uint_as_float(v[i]), sc, sum[ci][i]);
+                  else sum[ci][i] = (kb == 0 && jj == 0) ? __uint_as_float(v[i]) : sum[ci][i] + __uint_as_float(v[i]);
+                }
             }
           }
         }
@@ -512,6 +624,52 @@ __global__ void conv3x3_tc_pack_kernel(const float* __restrict__ w, int cin, int
   }
 }
 
+// 3xFP16 packing: same [kb][tap][h1|h2][cout][32] order with fp16 elements (64-byte rows), w * s_w = h1 + 2^-11 * h2, the
+// power-of-two s_w putting the layer's largest |w| in [2^14, 2^15); 1 / s_w goes to scale_out for the forward kernel.
+__global__ void conv3x3_tc_wmax_kernel(const float* __restrict__ w, int64_t n, unsigned int* __restrict__ out_bits) {
+  unsigned int m = 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(w[i]) & 0x7FFFFFFFu);
+  for (int o = 16; o >= 1; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out_bits, m);
+}
+
+__global__ void conv3x3_tc_pack_f16_kernel(const float* __restrict__ w, int cin, int cout_real, int cout, int kblocks, int s2d_c,
+                                           int s2d_chunks, const unsigned int* __restrict__ wmax_bits, __half* __restrict__ out,
+                                           float* __restrict__ scale_out) {
+  int E = (int)(*wmax_bits >> 23) - 127;
+  E = E < -100 ? -100 : (E > 100 ? 100 : E);
+  const float sw = __uint_as_float((uint32_t)(127 + 14 - E) << 23);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *scale_out = __uint_as_float((uint32_t)(127 - 14 + E) << 23);
+  const int64_t n = (int64_t)kblocks * 9 * cout * KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % KC);
+    const int co = (int)((i / KC) % cout);
+    const int tap = (int)((i / ((int64_t)KC * cout)) % 9);
+    const int kb = (int)(i / ((int64_t)KC * cout * 9));
+    float v = 0.f;
+    if (co < cout_real) {
+      if (s2d_c == 0) {
+        const int ci = kb * KC + c;
+        if (ci < cin) v = w[((size_t)tap * cin + ci) * cout_real + co];
+      } else {
+        const int py = kb / s2d_chunks, idx = (kb - py * s2d_chunks) * KC + c;
+        const int px = idx / s2d_c, ci = idx - px * s2d_c;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ky = 2 * dy + py, kx = 2 * dx + px;
+        if (dy >= 0 && dx >= 0 && ky <= 2 && kx <= 2 && px < 2) v = w[((size_t)(ky * 3 + kx) * cin + ci) * cout_real + co];
+      }
+    }
+    const float x = v * sw;
+    const __half h1 = __float2half_rn(x);
+    const __half h2 = __float2half_rn((x - __half2float(h1)) * 2048.f);
+    const size_t row_hi = ((size_t)(kb * 9 + tap) * 2 + 0) * cout + co;
+    const size_t row_lo = ((size_t)(kb * 9 + tap) * 2 + 1) * cout + co;
+    out[row_hi * KC + c] = h1;
+    out[row_lo * KC + c] = h2;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -559,8 +717,15 @@ inline int tc_pick_slices(int cout_pad, int64_t ntiles, int sms) {
   return best;
 }
 
+inline int64_t tc_plane_floats(int cin, int cout, int stride, int prec) {       // packed weight planes, in floats
+  const int64_t elems = (int64_t)tc_kblocks(cin, stride) * 9 * 2 * tc_cout_pad(cout) * KC;
+  return prec == M4D_CONV_PREC_3XFP16 ? elems / 2 : elems;
+}
+
 int tc_launch(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin, int cout,
-              int stride, float leaky_alpha, float* y, int y_pix_stride, int force_slices, cudaStream_t stream) {
+              int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int force_slices, cudaStream_t stream) {
+  const bool half = prec == M4D_CONV_PREC_3XFP16;
+  const float* w_scale = packed + tc_plane_floats(cin, cout, stride, prec);      // 3xFP16: 1 / s_w behind the planes
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled is not available from this driver");
@@ -606,11 +771,12 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   }
   {
     const cuuint64_t dims[2] = {KC, (cuuint64_t)kb * 9 * 2 * ctot};
-    const cuuint64_t strides[1] = {KC * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)KC * (half ? 2 : 4)};
     const cuuint32_t box[2] = {KC, (cuuint32_t)cout};         // one plane's rows of a slice; two loads per stage
     const cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&mw, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packed), dims, strides,
+                     box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       m4d_set_error("m4d_conv3x3_tc_fwd: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
       return M4D_ECUDA;
@@ -632,7 +798,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   }
   TcArgs a;
   a.bias = bias; a.y = y; a.h = oh; a.w = ow; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
-  a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha;
+  a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha; a.w_scale = w_scale;
   a.s2d_c = stride == 1 ? 0 : cin;
   a.s2d_chunks = stride == 1 ? 1 : 2 * cin / KC;
   a.cin = stride == 1 ? cin : 4 * cin;
@@ -647,33 +813,31 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.concat = cout <= 64 ? 1 : 0;
   a.nacc = a.concat ? 3 : 2;
   a.nsets = 2;
-  const size_t fixed = 1024 + (size_t)A_STAGES * 2 * A_SLOT + 2 * OUT_SLOT + 512;
-  const size_t stage = (size_t)2 * cout * 128;
+  const size_t fixed = 1024 + (size_t)A_STAGES * (half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32) + 2 * OUT_SLOT + 512;
+  const size_t stage = (size_t)2 * cout * (half ? 64 : 128);
   int nb = (int)((227 * 1024 - fixed) / stage);
   if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
   M4D_REQUIRE(nb >= 2, "m4d_conv3x3_tc_fwd: not enough shared memory for the weight pipeline");
   a.nb = nb;
   const size_t smem = fixed + (size_t)nb * stage;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, TcArgs);
+  static const KernelFn kernels[8] = {conv3x3_tc_kernel<false, false, false>, conv3x3_tc_kernel<false, true, false>,
+                                      conv3x3_tc_kernel<true, false, false>,  conv3x3_tc_kernel<true, true, false>,
+                                      conv3x3_tc_kernel<false, false, true>,  conv3x3_tc_kernel<false, true, true>,
+                                      conv3x3_tc_kernel<true, false, true>,   conv3x3_tc_kernel<true, true, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      m4d_set_error("m4d_conv3x3_tc_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      return M4D_ECUDA;
+    for (int i = 0; i < 8; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        m4d_set_error("m4d_conv3x3_tc_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+        return M4D_ECUDA;
+      }
     }
     attr_set = true;
   }
   const int grid = a.nitems < m4d_sm_count() ? a.nitems : m4d_sm_count();
-  if (stride == 1) {
-    if (a.concat) conv3x3_tc_kernel<false, true><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
-    else conv3x3_tc_kernel<false, false><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
-  } else {
-    if (a.concat) conv3x3_tc_kernel<true, true><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
-    else conv3x3_tc_kernel<true, false><<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
-  }
+  kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)]<<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
 }
@@ -682,29 +846,48 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
 
 extern "C" {
 
-int64_t m4d_conv3x3_tc_packed_floats_s(int cin, int cout, int stride) {
-  if (!tc_shape_ok(cin, cout, stride)) return 0;
-  return (int64_t)tc_kblocks(cin, stride) * 9 * 2 * tc_cout_pad(cout) * KC;
+int64_t m4d_conv3x3_tc_packed_floats_p(int cin, int cout, int stride, int prec) {
+  if (!tc_shape_ok(cin, cout, stride) || (prec != M4D_CONV_PREC_3XTF32 && prec != M4D_CONV_PREC_3XFP16)) return 0;
+  return tc_plane_floats(cin, cout, stride, prec) + 32;           // + the weight scale (3xFP16) and its scratch word
 }
 
-int m4d_conv3x3_tc_pack_s(const float* kernel_hwio, int cin, int cout, int stride, float* packed, void* stream) {
+int m4d_conv3x3_tc_pack_p(const float* kernel_hwio, int cin, int cout, int stride, int prec, float* packed, void* stream) {
   M4D_REQUIRE(kernel_hwio && packed, "m4d_conv3x3_tc_pack: null pointer");
   M4D_REQUIRE(tc_shape_ok(cin, cout, stride),
               "m4d_conv3x3_tc_pack: unsupported shape cin=%d cout=%d stride=%d (cout <= 256; stride 2 needs cin %% 16 == 0)", cin, cout, stride);
+  M4D_REQUIRE(prec == M4D_CONV_PREC_3XTF32 || prec == M4D_CONV_PREC_3XFP16, "m4d_conv3x3_tc_pack: unknown precision mode %d", prec);
   const int kb = tc_kblocks(cin, stride);
   const int cp = tc_cout_pad(cout);
   const int64_t n = (int64_t)kb * 9 * cp * KC;
   const int grid = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-  conv3x3_tc_pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, cin, cout, 0, cout, cp, kb, stride == 1 ? 0 : cin,
-                                                                  stride == 1 ? 1 : 2 * cin / KC, packed);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* tail = packed + tc_plane_floats(cin, cout, stride, prec);
+  if (prec == M4D_CONV_PREC_3XTF32) {
+    conv3x3_tc_pack_kernel<<<grid, 256, 0, st>>>(kernel_hwio, cin, cout, 0, cout, cp, kb, stride == 1 ? 0 : cin, stride == 1 ? 1 : 2 * cin / KC,
+                                                 packed);
+    M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
+    return M4D_OK;
+  }
+  cudaError_t e = cudaMemsetAsync(tail, 0, 32 * sizeof(float), st);
+  if (e != cudaSuccess) {
+    m4d_set_error("m4d_conv3x3_tc_pack: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return M4D_ECUDA;
+  }
+  const int64_t nw = (int64_t)9 * cin * cout;
+  conv3x3_tc_wmax_kernel<<<(int)((nw + 255) / 256 < 1024 ? (nw + 255) / 256 : 1024), 256, 0, st>>>(kernel_hwio, nw,
+                                                                                                  reinterpret_cast<unsigned int*>(tail + 1));
+  M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack(max)");
+  conv3x3_tc_pack_f16_kernel<<<grid, 256, 0, st>>>(kernel_hwio, cin, cout, cp, kb, stride == 1 ? 0 : cin, stride == 1 ? 1 : 2 * cin / KC,
+                                                   reinterpret_cast<const unsigned int*>(tail + 1), reinterpret_cast<__half*>(packed), tail);
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_pack");
   return M4D_OK;
 }
 
-int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
-                          int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream) {
+int m4d_conv3x3_tc_fwd_p(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                         int cout, int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream) {
   M4D_REQUIRE(x && packed && bias && y, "m4d_conv3x3_tc_fwd: null pointer");
   M4D_REQUIRE(b > 0 && h > 0 && w > 0, "m4d_conv3x3_tc_fwd: non-positive size");
+  M4D_REQUIRE(prec == M4D_CONV_PREC_3XTF32 || prec == M4D_CONV_PREC_3XFP16, "m4d_conv3x3_tc_fwd: unknown precision mode %d", prec);
   const bool s2_ok = stride != 2 || (h % 2 == 0 && w % 2 == 0 && x_pix_stride == cin);
   if (!tc_shape_ok(cin, cout, stride) || !s2_ok || x_pix_stride % 4 != 0 || x_pix_stride < cin || y_pix_stride < cout ||
       (reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(packed) & 15u)) {
@@ -712,9 +895,20 @@ int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed,
                   stride, h, w, x_pix_stride, y_pix_stride);
     return M4D_ENOTSUP;
   }
-  return tc_launch(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, leaky_alpha, y, y_pix_stride, slices, (cudaStream_t)stream);
+  return tc_launch(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, prec, leaky_alpha, y, y_pix_stride, slices, (cudaStream_t)stream);
 }
 
+int64_t m4d_conv3x3_tc_packed_floats_s(int cin, int cout, int stride) {
+  return m4d_conv3x3_tc_packed_floats_p(cin, cout, stride, M4D_CONV_PREC_3XTF32);
+}
+int m4d_conv3x3_tc_pack_s(const float* kernel_hwio, int cin, int cout, int stride, float* packed, void* stream) {
+  return m4d_conv3x3_tc_pack_p(kernel_hwio, cin, cout, stride, M4D_CONV_PREC_3XTF32, packed, stream);
+}
+int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
+                          int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, int slices, void* stream) {
+  return m4d_conv3x3_tc_fwd_p(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, M4D_CONV_PREC_3XTF32, leaky_alpha, y, y_pix_stride,
+                              slices, stream);
+}
 int m4d_conv3x3_tc_fwd_s(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin,
                          int cout, int stride, float leaky_alpha, float* y, int y_pix_stride, void* stream) {
   return m4d_conv3x3_tc_fwd_ex(x, x_pix_stride, packed, bias, b, h, w, cin, cout, stride, leaky_alpha, y, y_pix_stride, 0, stream);

@@ -61,11 +61,17 @@ def _new_traj_flag(new_traj):
     return bool(new_traj[0])
 
 
+# precision mode of the tensor-core convs (include/m4d.h M4D_CONV_PREC_*): 0 = 3xTF32, 1 = 3xFP16 (scaled fp16 hi/lo planes:
+# same error class, twice the tensor-core rate).  M4D_CONV_PREC in the environment overrides the default.
+DEFAULT_CONV_PREC = int(os.environ.get("M4D_CONV_PREC", "1"))
+
+
 class _Conv2D:
     """ks.layers.Conv2D(filters, 3, strides, padding='same') with fused bias + optional leaky_relu (libm4d)."""
 
-    def __init__(self, filters, strides=1):
+    def __init__(self, filters, strides=1, prec=None):
         self.filters, self.strides = filters, strides
+        self.prec = DEFAULT_CONV_PREC if prec is None else prec
         self.kernel = None          # [3,3,cin,cout] HWIO
         self.packed = None          # TF32 hi/lo planes for the tcgen05 path (m4d_conv3x3_tc_pack)
         self.tc_min_cin = 16        # thinner inputs (the RGB conv) stay on the FFMA2 kernel
@@ -81,10 +87,10 @@ class _Conv2D:
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         # tensor-core path (stride 1, or stride 2 with cin % 16 == 0; cout <= 256): TF32 hi/lo planes packed once per layer
         self.packed = None
-        n = L.lib.m4d_conv3x3_tc_packed_floats_s(k.shape[2], self.filters, self.strides)
+        n = L.lib.m4d_conv3x3_tc_packed_floats_p(k.shape[2], self.filters, self.strides, self.prec)
         if n > 0:
             self.packed = torch.empty(n, dtype=torch.float32, device=k.device)
-            L.check(L.lib.m4d_conv3x3_tc_pack_s(L.ptr(k), k.shape[2], self.filters, self.strides, L.ptr(self.packed), L.stream()))
+            L.check(L.lib.m4d_conv3x3_tc_pack_p(L.ptr(k), k.shape[2], self.filters, self.strides, self.prec, L.ptr(self.packed), L.stream()))
 
     def out_shape(self, x):
         b, h, w, _ = x.shape
@@ -112,8 +118,8 @@ class _Conv2D:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            L.check(L.lib.m4d_conv3x3_tc_fwd_ex(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
-                                                self.strides, float(alpha), L.ptr(out), ys, int(slices), L.stream()))
+            L.check(L.lib.m4d_conv3x3_tc_fwd_p(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
+                                               self.strides, self.prec, float(alpha), L.ptr(out), ys, int(slices), L.stream()))
             if self.events is not None:
                 ev1.record()
                 self.events.append((ev0, ev1))

@@ -534,6 +534,52 @@ def test_conv3x3_tcgen05_output_channel_slices(cfg):
     assert ran >= 2
 
 
+@pytest.mark.parametrize("cfg", [(1, 16, 8, 32, 16, 1), (2, 16, 16, 64, 128, 1), (1, 24, 80, 122, 128, 1), (2, 13, 21, 128, 96, 1),
+                                 (1, 6, 20, 470, 128, 1), (1, 33, 47, 96, 64, 1), (1, 12, 40, 238, 32, 1), (1, 20, 9, 16, 16, 1),
+                                 (2, 19, 23, 16, 5, 1), (1, 16, 8, 40, 20, 1), (2, 32, 48, 16, 16, 2), (1, 20, 36, 64, 64, 2),
+                                 (1, 12, 40, 192, 192, 2), (1, 34, 18, 48, 80, 2), (1, 12, 40, 128, 192, 1)])
+@pytest.mark.parametrize("dyn", ["unit", "wide"])
+def test_conv3x3_tcgen05_3xfp16_vs_oracle(cfg, dyn):
+    """The 3xFP16 mode of the tensor-core conv (operands scaled per layer / per tile-k-block and split into fp16 h1 + 2^-11 h2;
+    hi*hi + hi*lo + lo*hi in fp32) is in the same error class as 3xTF32 and the FFMA kernel: 1e-5 of the tensor scale against
+    the oracle, 4e-6 against fp64 - also when the input's magnitude varies over 12 orders between image regions and
+    channels ("wide"), which fp16's exponent range alone could not represent."""
+    m = _m4d()
+    b, h, w, cin, cout, stride = cfg
+    g = torch.Generator().manual_seed(cin * cout + h)
+    x = torch.randn(b, h, w, cin, generator=g)
+    if dyn == "wide":
+        x = x * torch.exp(torch.randn(b, h, 1, 1, generator=g) * 6.0) * torch.exp(torch.randn(1, 1, 1, cin, generator=g) * 3.0)
+        x[:, : h // 4] = 0.0                                                     # an all-zero region: scale falls back to 1
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    k[..., : cout // 3] *= 1e-3                                                  # output channels with tiny weights
+    bias = torch.randn(cout, generator=g) * 0.1
+    from m4depth_b200.m4depth_network import _Conv2D
+    conv = _Conv2D(cout, stride, prec=1)
+    conv.assign(k, bias, "cuda")
+    xs = (cin + 3) // 4 * 4
+    if stride == 1:
+        wide = torch.zeros(b, h, w, xs + 4)
+        wide[..., :cin] = x
+        xin = cu(wide)[..., :cin]
+    else:
+        xin = cu(x)
+    tc = conv(xin, alpha=0.1, algo=2).clone()
+    pad = (0, 1, 0, 1) if stride == 2 else (1, 1, 1, 1)
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), pad)
+    ref64 = torch.nn.functional.conv2d(xp, k.double().permute(3, 2, 0, 1), bias.double(), stride=stride)
+    ref64 = torch.nn.functional.leaky_relu(ref64, 0.1).permute(0, 2, 3, 1)
+    # error measured against the local magnitude of the sum (|x| * |w| convolved), so that the small-magnitude regions of the
+    # "wide" input are held to the same relative standard as the large ones
+    mag = torch.nn.functional.conv2d(xp.abs(), k.double().abs().permute(3, 2, 0, 1), bias.double().abs(), stride=stride).permute(0, 2, 3, 1)
+    err = ((tc.cpu().double() - ref64).abs() / (mag + 1e-30)).max()
+    print(f"cin={cin} cout={cout} s{stride} {dyn}: max error / local magnitude {float(err):.2e}")
+    assert float(err) < (2e-6 if dyn == "unit" else 1e-5)
+    if dyn == "unit":
+        want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, stride))
+        np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+
+
 def test_conv3x3_tcgen05_wide_output_split():
     """cout = 192 (> 128 TMEM-friendly columns): output channels sliced over two CTAs per tile, stride 1 (128->192)."""
     m = _m4d()
