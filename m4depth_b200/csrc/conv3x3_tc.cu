@@ -30,12 +30,12 @@ constexpr int HALO_W = TILE_W + 2, HALO_H = TILE_H + 2;
 constexpr int KC = 32;                                         // channels per k-block (128-byte rows)
 constexpr int A_BYTES = HALO_W * HALO_H * KC * 4;              // 23040: one halo plane as landed by TMA
 constexpr int A_SLOT = (A_BYTES + 1023) / 1024 * 1024;         // 23552
-constexpr int A_STAGES = 2;
+constexpr int MAX_A_STAGES = 3;                                // halo stages: 3 where shared memory allows (thin layers), else 2
 // 3xFP16 mode: the fp32 halo lands in the first A_SLOT bytes of a stage, its two fp16 planes (64-byte rows) follow
 constexpr int AH_PLANE = (HALO_W * HALO_H * KC * 2 + 1023) / 1024 * 1024;   // 12288
 constexpr int A_STAGE_BYTES_F32 = 2 * A_SLOT;
 constexpr int A_STAGE_BYTES_F16 = A_SLOT + 2 * AH_PLANE;
-constexpr int MAX_B_STAGES = 6;
+constexpr int MAX_B_STAGES = 32;
 constexpr int OUT_SLOT = 128 * 128;                            // one [128 px][32 ch] fp32 staging tile
 constexpr int NTHREADS = 512;
 
@@ -46,6 +46,8 @@ struct TcArgs {
   int cout_real;                    // channels actually stored
   int cin;                          // real input channels: k-steps of the last k-block that are all zero fill are skipped
   int tiles_x, tiles_y, ntiles;
+  int na;                           // halo stages in flight (2 or 3)
+  int b_resident;                   // all of the layer's weight slabs fit in the ring: loaded once per CTA, never released
   int nslices, nitems;              // output-channel slices of width cout per tile; work items = ntiles * nslices
   int ctot;                         // rows per weight plane in the packed buffer = all output channels rounded up to 16
   int nb;                           // weight-slab stages that fit in shared memory (3 at Cout = 128 ... 6)
@@ -233,25 +235,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   constexpr uint32_t A_STAGE = HALF ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;               // swizzled tiles need 1024-byte alignment
   const uint32_t b_stage_bytes = 2u * (uint32_t)a.cout * ROWB;                // hi + lo planes of [Cout][32]
-  const uint32_t sA = smem0;                                                  // [A_STAGES][A_STAGE]
-  const uint32_t sOut = sA + A_STAGES * A_STAGE;                              // [2][128 px][32 ch] staging for the TMA stores
+  const uint32_t sA = smem0;                                                  // [na][A_STAGE]
+  const uint32_t sOut = sA + (uint32_t)a.na * A_STAGE;                              // [2][128 px][32 ch] staging for the TMA stores
   const uint32_t sB = sOut + 2 * OUT_SLOT;                                    // [nb][b_stage_bytes]
   const uint32_t sBar = sB + (uint32_t)a.nb * b_stage_bytes;
-  const uint32_t a_full = sBar, a_ready = sBar + 8 * A_STAGES, a_empty = sBar + 16 * A_STAGES;
-  const uint32_t b_full = sBar + 24 * A_STAGES, b_empty = b_full + 8 * MAX_B_STAGES;
+  const uint32_t a_full = sBar, a_ready = sBar + 8 * MAX_A_STAGES, a_empty = sBar + 16 * MAX_A_STAGES;
+  const uint32_t b_full = sBar + 24 * MAX_A_STAGES, b_empty = b_full + 8 * MAX_B_STAGES;
   const uint32_t acc_full = b_empty + 8 * MAX_B_STAGES, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
-  const uint32_t s_max = tmem_slot + 16;                                      // [A_STAGES] uint: max |x| bits of the landed halo
-  const uint32_t s_scale = s_max + 16;                                        // [4] float: 1 / (s_x * s_w) of k-block ka & 3
+  const uint32_t s_max = tmem_slot + 16;                                      // [MAX_A_STAGES (4 slots)] uint: max |x| bits of the landed halo
+  const uint32_t s_scale = s_max + 16;                                        // [8] float: 1 / (s_x * s_w) of k-block ka & 7 (8 slots: the splitters run up to 3 k-blocks ahead of the MMAs, the epilogue one behind)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KB = a.kblocks, NB = a.nb;
+  const int KB = a.kblocks, NB = a.nb, NA = a.na;
+  // Up to 64 output channels one epilogue group (warps 8-11) owns both 32-column chunks and the other four warps (12-15)
+  // join the splitters: with few columns per MMA the split, not the tensor pipe, paces a k-block.
+  const bool wide_split = a.cout <= 64;
+  const uint32_t nsplit = wide_split ? 256u : 128u;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < A_STAGES; ++s) {
+    for (int s = 0; s < MAX_A_STAGES; ++s) {
       mbar_init(a_full + 8 * s, 1);
-      mbar_init(a_ready + 8 * s, 128);
+      mbar_init(a_ready + 8 * s, nsplit);
       mbar_init(a_empty + 8 * s, 1);
     }
     for (int s = 0; s < MAX_B_STAGES; ++s) {
@@ -260,10 +266,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 8);          // one lane of each of the 8 epilogue warps
+      mbar_init(acc_empty + 8 * s, wide_split ? 4 : 8);   // one lane of each epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < A_STAGES; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
+    for (int i = 0; i < MAX_A_STAGES; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
   }
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
@@ -287,8 +293,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
       for (int kb = 0; kb < KB; ++kb, ++ka) {
-        const int s = ka % A_STAGES;
-        mbar_wait(a_empty + 8 * s, ((ka / A_STAGES) & 1) ^ 1);
+        const int s = ka % NA;
+        mbar_wait(a_empty + 8 * s, ((ka / NA) & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(a_full + 8 * s, A_BYTES);
           if (!S2D) {
@@ -304,15 +310,16 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   } else if (warp == 1) {
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
-    int it = 0;
+    int s = 0;                                                       // ring position and phase, advanced incrementally:
+    uint32_t ph = 0;                                                 // (a run-time % and / per tap cost more than the tap's MMAs)
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      if (a.b_resident && item != (int)blockIdx.x) break;           // resident weights: one pass fills the ring for every tile
       const int n0 = (item % a.nslices) * a.cout;                    // first output channel of this item's slice
       for (int kb = 0; kb < KB; ++kb) {
         const KbTaps tp = kb_taps<S2D, KS>(a, kb);
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky)
-          for (int kx = tp.kx_lo; kx <= tp.kx_hi(); ++kx, ++it) {
-            const int s = it % NB;
-            mbar_wait(b_empty + 8 * s, ((it / NB) & 1) ^ 1);
+          for (int kx = tp.kx_lo; kx <= tp.kx_hi(); ++kx) {
+            if (!a.b_resident) mbar_wait(b_empty + 8 * s, ph ^ 1);
             if (elect_one()) {
               mbar_expect_tx(b_full + 8 * s, b_stage_bytes);
               const int row = (kb * 9 + ky * 3 + kx) * 2 * a.ctot + n0;   // the slice's rows of the hi plane; lo plane: + ctot
@@ -320,6 +327,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               tma_load_2d(sB + s * b_stage_bytes + (uint32_t)a.cout * ROWB, &tmap_w, b_full + 8 * s, 0, row + a.ctot);
             }
             __syncwarp();
+            if (++s == NB) { s = 0; ph ^= 1u; }
           }
       }
     }
@@ -341,36 +349,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // the adjacent [W_hi ; W_lo] planes as one N = 2*Cout operand.  With small N the MMAs are bound by the 4 KB A-operand
     // read from shared memory (128 B/clk), so one A pass less per k-step is 25-30 % of the layer.
     const uint32_t ncol = (uint32_t)a.cout;
-    int ka = 0, it = 0;
+    int ka = 0, sb = 0, sa = 0;
+    uint32_t bph = 0, aph = 0;
+    const uint32_t ring_mask = a.b_resident ? 0u : 1u;               // resident weights: every slab's barrier completed phase 0 for good
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+      if (a.b_resident) sb = 0;                                      // slab = position within the tile
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
         const int set = ka & 1;
         mbar_wait(acc_empty + 8 * set, ((ka >> 1) & 1) ^ 1);            // epilogue has drained this set
         const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
         const uint32_t d_corr = d_set + (CONCAT ? 2u : 1u) * ncol;
-        const int sa = ka % A_STAGES;
-        mbar_wait(a_ready + 8 * sa, (ka / A_STAGES) & 1);
+        mbar_wait(a_ready + 8 * sa, aph);
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
         const uint64_t dA_hi = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT, HALO_W * 64) : umma_desc(sA + sa * A_STAGE, HALO_W * 128);
         const uint64_t dA_lo = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT + AH_PLANE, HALO_W * 64)
                                     : umma_desc(sA + sa * A_STAGE + A_SLOT, HALO_W * 128);
         const KbTaps tp = kb_taps<S2D, KS>(a, kb);
         const int kx_hi = tp.kx_hi();
+        const int ntap = kx_hi - (S2D ? 1 : 0) + 1;                     // taps per window row that carry weights
 #pragma unroll 1
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky) {
+          // One elected region per window ROW (up to three taps): the per-region cost - barrier polls, election, moving
+          // descriptors into uniform registers - was ~70 instructions per tap and, at ~7 clocks each, longer than the six
+          // fp16 MMAs of a 128-column tap (measured: the issuer, not the tensor pipe, set the pace of every layer).
+          int sbs[3];
+          {
+            int s_ = sb;
+            uint32_t ph_ = bph;
 #pragma unroll
-          for (int kx = S2D ? 1 : 0; kx < 3; ++kx) {
-            if (S2D && kx > kx_hi) break;
-            const int nk = tp.nk(kx);
-            const int sb = it % NB;
-            mbar_wait(b_full + 8 * sb, (it / NB) & 1);
-            ++it;
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t dB_hi = HALF ? umma_desc64(sB + sb * b_stage_bytes, 512) : umma_desc(sB + sb * b_stage_bytes, 1024);
+            for (int j = 0; j < 3; ++j)
+              if (j < ntap) {
+                sbs[j] = s_;
+                mbar_wait(b_full + 8 * s_, ph_ & ring_mask);
+                if (++s_ == NB) { s_ = 0; ph_ ^= 1u; }
+              }
+            sb = s_;
+            bph = ph_;
+          }
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              if (j >= ntap) break;
+              const int kx = (S2D ? 1 : 0) + j;
+              const int nk = tp.nk(kx);
+              const uint64_t dB_hi = HALF ? umma_desc64(sB + sbs[j] * b_stage_bytes, 512) : umma_desc(sB + sbs[j] * b_stage_bytes, 1024);
               const uint32_t tap16 = ((uint32_t)(ky * HALO_W + kx) * ROWB) >> 4;
-              const uint32_t later = (ky > tp.ky_lo || kx > (S2D ? 1 : 0)) ? 1u : 0u;     // past the first tap of the k-block
+              const uint32_t later = (ky > tp.ky_lo || j > 0) ? 1u : 0u;     // past the first tap of the k-block
 #pragma unroll
               for (int ks = 0; ks < KC / KS; ++ks) {              // a k-step is 32 bytes of a row in either format
                 if (ks >= nk) break;
@@ -395,29 +421,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                   tc_mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
                 }
               }
-              tc_commit(b_empty + 8 * sb);
-              if (ky == tp.ky_hi && kx == kx_hi) {
-                tc_commit(a_empty + 8 * sa);
-                tc_commit(acc_full + 8 * set);
-              }
+              tc_commit(b_empty + 8 * sbs[j]);                      // (nobody waits for it when the weights are resident)
             }
-            __syncwarp();
+            if (ky == tp.ky_hi) {
+              tc_commit(a_empty + 8 * sa);
+              tc_commit(acc_full + 8 * set);
+            }
           }
+          __syncwarp();
         }
+        if (++sa == NA) { sa = 0; aph ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes
-    const int t = threadIdx.x - 128;
+  } else if ((warp >= 4 && warp < 8) || (wide_split && warp >= 12)) {
+    // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
+    const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
+    const int NS = (int)nsplit;
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
       for (int kb = 0; kb < KB; ++kb, ++ka) {
-        const int s = ka % A_STAGES;
-        mbar_wait(a_full + 8 * s, (ka / A_STAGES) & 1);
+        const int s = ka % NA;
+        mbar_wait(a_full + 8 * s, (ka / NA) & 1);
         const uint32_t hi_p = sA + s * A_STAGE, lo_p = hi_p + A_SLOT;
         if (!HALF) {
 #pragma unroll 4
-          for (int i = t; i < A_BYTES / 16; i += 128) {
+          for (int i = t; i < A_BYTES / 16; i += NS) {
             const uint4 v = lds128(hi_p + i * 16);
             uint4 hi, lo;
             split_tf32(v.x, hi.x, lo.x);
@@ -432,12 +460,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // row r lives at c ^ (r & 7)) -> one 16-byte chunk of each fp16 plane (SWIZZLE_64B: chunk j of row r at
           // j ^ ((r >> 1) & 3); both follow from the absolute shared-memory address, the planes are 1024-byte aligned)
           constexpr int NU = HALO_W * HALO_H * 4, UPT = (NU + 127) / 128;
+          // 8-channel units that hold input channels (the rest of a partial last k-block is TMA zero fill no MMA reads)
+          const int rem_ch = (S2D ? 4 * a.s2d_c : a.cin) - kb * KC;
+          const int jmax = rem_ch >= KC ? 4 : (rem_ch + 15) / 16 * 2;
           uint4 va[UPT], vb[UPT];
           uint32_t mx = 0u;
 #pragma unroll
           for (int u = 0; u < UPT; ++u) {
-            const int idx = t + u * 128;
-            if (idx < NU) {
+            const int idx = t + u * NS;
+            if (idx < NU && (idx & 3) < jmax) {
               const int px = idx >> 2, j = idx & 3;
               const uint32_t row = hi_p + (uint32_t)px * 128u;
               va[u] = lds128(row + (uint32_t)(((2 * j) ^ (px & 7)) * 16));
@@ -450,7 +481,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
           if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(mx) : "memory");
-          asm volatile("bar.sync 3, 128;" ::: "memory");
+          asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory");
           uint32_t mbits;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(s_max + 4 * s) : "memory");
           // s_x = 2^(14 - E) with E the exponent of the maximum (so max * s_x is in [2^14, 2^15)); exponents are clamped so that
@@ -458,17 +489,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           int E = (int)(mbits >> 23) - 127;
           E = E < -100 ? -100 : (E > 100 ? 100 : E);
           const float sx = __uint_as_float((uint32_t)(127 + 14 - E) << 23);
-          asm volatile("bar.sync 3, 128;" ::: "memory");                 // everyone has read the maximum
+          asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory");      // everyone has read the maximum
           if (t == 0) {
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(0u) : "memory");
             const float inv = __uint_as_float((uint32_t)(127 - 14 + E) << 23) * __ldg(a.w_scale);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_scale + 4 * (ka & 3)), "f"(inv) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_scale + 4 * (ka & 7)), "f"(inv) : "memory");
           }
           const uint32_t h1_p = hi_p + A_SLOT, h2_p = h1_p + AH_PLANE;
 #pragma unroll
           for (int u = 0; u < UPT; ++u) {
-            const int idx = t + u * 128;
-            if (idx < NU) {
+            const int idx = t + u * NS;
+            if (idx < NU && (idx & 3) < jmax) {
               const int px = idx >> 2, j = idx & 3;
               const float x[8] = {__uint_as_float(va[u].x) * sx, __uint_as_float(va[u].y) * sx, __uint_as_float(va[u].z) * sx,
                                   __uint_as_float(va[u].w) * sx, __uint_as_float(vb[u].x) * sx, __uint_as_float(vb[u].y) * sx,
@@ -491,7 +522,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
         mbar_arrive(a_ready + 8 * s);
       }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && (!wide_split || warp < 12)) {
     // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant, group g the
     // 32-column chunks g and g+2.  After every k-block the group adds that k-block's accumulators into its register sums and
     // hands the set back; after the last one it applies bias + leaky_relu and stores through its staging tile.
@@ -513,11 +544,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
         float inv_main = 1.f;                                       // 3xFP16: 1 / (s_x * s_w) of this k-block, cross terms * 2^-11
-        if (HALF) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_main) : "r"(s_scale + 4 * (ka & 3)) : "memory");
+        if (HALF) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_main) : "r"(s_scale + 4 * (ka & 7)) : "memory");
         const float inv_cross = inv_main * (1.0f / 2048.0f);
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          const int c0 = (grp + 2 * ci) * 32;
+          const int c0 = (wide_split ? ci : grp + 2 * ci) * 32;
           if (c0 < a.cout) {
             const int nc = a.cout - c0 >= 32 ? 32 : 16;
             for (int jj = 0; jj < a.nacc; ++jj) {                   // hi*hi, then the cross-term accumulator(s)
@@ -544,8 +575,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
-        const int c0 = (grp + 2 * ci) * 32;
-        if (grp + 2 * ci >= nchunks) continue;
+        const int c0 = (wide_split ? ci : grp + 2 * ci) * 32;
+        if ((wide_split ? ci : grp + 2 * ci) >= nchunks) continue;
         const int nc = a.cout - c0 >= 32 ? 32 : 16;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -723,8 +754,9 @@ inline int64_t tc_plane_floats(int cin, int cout, int stride, int prec) {       
 }
 
 int tc_launch(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w, int cin, int cout,
-              int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int force_slices, cudaStream_t stream) {
+              int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int force, cudaStream_t stream) {
   const bool half = prec == M4D_CONV_PREC_3XFP16;
+  const int force_slices = force & 15, force_na = (force >> 4) & 3;      // tuning: slices | halo stages << 4
   const float* w_scale = packed + tc_plane_floats(cin, cout, stride, prec);      // 3xFP16: 1 / s_w behind the planes
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -813,12 +845,32 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.concat = cout <= 64 ? 1 : 0;
   a.nacc = a.concat ? 3 : 2;
   a.nsets = 2;
-  const size_t fixed = 1024 + (size_t)A_STAGES * (half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32) + 2 * OUT_SLOT + 512;
+  // halo stages: a k-block's chain TMA load -> split -> MMAs -> release is several thousand clocks of latency; with few
+  // output channels the MMAs are short and two stages leave the tensor pipe waiting, so take a third where the weight
+  // ring still gets >= 4 stages
+  const size_t a_stage = half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
   const size_t stage = (size_t)2 * cout * (half ? 64 : 128);
+  int na = force_na > 0 ? force_na : 2;                           // (a third stage measured no gain: the weight ring was the limit)
+  size_t fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024;
+  if (na > 2 && (227 * 1024 < fixed + 4 * stage)) {
+    na = 2;
+    fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024;
+  }
+  M4D_REQUIRE(na >= 2 && na <= MAX_A_STAGES && 227 * 1024 >= fixed + 2 * stage, "m4d_conv3x3_tc_fwd: not enough shared memory for the pipeline");
   int nb = (int)((227 * 1024 - fixed) / stage);
   if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
-  M4D_REQUIRE(nb >= 2, "m4d_conv3x3_tc_fwd: not enough shared memory for the weight pipeline");
   a.nb = nb;
+  a.na = na;
+  // weight slabs a tile streams through the ring: (k-block, tap) pairs that carry weights
+  int slabs = 0;
+  for (int k = 0; k < kb; ++k) {
+    if (stride == 1) { slabs += 9; continue; }
+    const int chunks = 2 * cin / KC, py = k / chunks, left = cin - (k - py * chunks) * KC;
+    slabs += (py ? 1 : 2) * (left > 0 ? 2 : 1);
+  }
+  // Thin layers issue a tap's MMAs in ~100-200 clocks, far less than the latency of the TMA load that refills its stage, so
+  // the ring is deep (up to 32 slabs) and, where the whole layer fits, loaded once per CTA instead of once per tile.
+  a.b_resident = (nslices == 1 && slabs <= nb) ? 1 : 0;
   const size_t smem = fixed + (size_t)nb * stage;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, TcArgs);
   static const KernelFn kernels[8] = {conv3x3_tc_kernel<false, false, false>, conv3x3_tc_kernel<false, true, false>,
