@@ -312,9 +312,12 @@ def run_ours(args, rank, world, local):
             traffic = None
     cpu_fps, cpu = cpu_oracle_fps()
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
-    # tensor roofline of the dominant kernel by time: 3xTF32 costs three TF32 MMAs per product and TF32 runs at half the
-    # bf16 rate, so the fp32-faithful ceiling is bf16_peak / 6 on the 2*9*Cin*Cout*h*w figure (sustained peak: the kernel
-    # runs inside a long step)
+    # tensor roofline of the dominant kernel by time: every product costs three MMAs (hi*hi + hi*lo + lo*hi).  In the default
+    # 3xFP16 mode they are kind::f16 MMAs, so the fp32-faithful ceiling is bf16/fp16_peak / 3 on the 2*9*Cin*Cout*h*w figure; in
+    # the 3xTF32 mode (M4D_CONV_PREC=0) TF32 runs at half that rate: peak / 6.  Sustained peak: the kernel runs inside a long step.
+    from m4depth_b200.m4depth_network import DEFAULT_CONV_PREC
+    mma_per_peak = 3.0 if DEFAULT_CONV_PREC == 1 else 6.0
+    mode = "3xFP16 (scaled fp16 hi/lo planes, kind::f16)" if DEFAULT_CONV_PREC == 1 else "3xTF32"
     bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     conv_flops = 2.0 * 9 * 128 * 128 * (H // 2) * (W // 2) * b
     conv_avg = sum(conv_ms) / len(conv_ms)
@@ -327,6 +330,7 @@ def run_ours(args, rank, world, local):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": b * world, "height": H, "width": W, "levels": LEVELS,
                    "search_range": SEARCH, "weights": "random He-normal (seed 7), checkpoint key layout",
+                   "conv_precision": mode + ": fp32 in / fp32 out, every product as hi*hi + hi*lo + lo*hi with fp32 accumulation",
                    "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "l2": "inputs larger than L2: each step streams >1 GB of activations (level-1 refiner maps are 503 MB each) "
                          "through a 126 MB L2; no explicit flush", "outputs_finite": finite},
@@ -339,13 +343,14 @@ def run_ours(args, rank, world, local):
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": pscv_avg * 1e3,
                      "min_launch_us": pscv_ms[0] * 1e3, "launches_timed": len(pscv_ms), "peak_source": peak_src,
                      "how": "CUDA events around the launch inside K eagerly executed full steps (in situ, caches as the pipeline leaves them)"},
-        "roofline_conv": {"kernel": "conv3x3_tc_kernel (tcgen05 3xTF32 implicit GEMM), DispRefiner 128->128 at level 1: 192x640, b=8 "
-                                    "(refiner convs = ~60 % of the step)",
-                          "bound": "tensor", "achieved": conv_achieved, "peak": bf16_peak / 6.0, "unit": "TFLOP/s (fp32-equivalent: 2*9*Cin*Cout*h*w)",
-                          "frac": conv_achieved / (bf16_peak / 6.0), "tf32_tflops_executed": 3.0 * conv_achieved,
+        "roofline_conv": {"kernel": f"conv3x3_tc_kernel (tcgen05 {mode} implicit GEMM), DispRefiner 128->128 at level 1: 192x640, b=8 "
+                                    "(the largest single launch; the tensor-core convs are ~80 % of the step)",
+                          "bound": "tensor", "achieved": conv_achieved, "peak": bf16_peak / mma_per_peak,
+                          "unit": "TFLOP/s (fp32-equivalent: 2*9*Cin*Cout*h*w)",
+                          "frac": conv_achieved / (bf16_peak / mma_per_peak), "mma_tflops_executed": 3.0 * conv_achieved,
                           "avg_launch_us": conv_avg * 1e3, "min_launch_us": conv_ms[0] * 1e3, "launches_timed": len(conv_ms),
-                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 6 (TF32 = bf16/2, three MMAs per product), of measured"
-                                         if peaks else "fallback 1400 bf16 TFLOP/s / 6, of fallback",
+                          "peak_source": (f"MEASURED_PEAKS.json bf16_tflops_sustained / {mma_per_peak:.0f} (three MMAs per product), of measured"
+                                          if peaks else f"fallback 1400 bf16 TFLOP/s / {mma_per_peak:.0f}, of fallback"),
                           "how": "CUDA events around the launch inside K eagerly executed full steps"},
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
