@@ -143,6 +143,12 @@ int m4d_group_l2norm(const float* in, int npix, int c, int cuts, float* out, voi
  * 2*b*c doubles (need not be initialised); leaky_alpha != 1 additionally applies leaky_relu (:84). */
 int m4d_domain_norm(const float* x, int b, int h, int w, int c, const float* scale, const float* bias,
                     float leaky_alpha, double* stats_ws, float* out, void* stream);
+/* FeaturePyramid level 0 in one call (m4depth_network.py:79-84): y = leaky(DN(conv3x3_same(x) + conv_bias)) for the 3-channel
+ * image and the 16-channel first layer.  The conv output is never stored: both DN passes recompute it from the image (same FMA
+ * chain), so the statistics describe exactly the values that are normalised.  x [b,h,w,>=3] with pixel stride x_pix_stride;
+ * kernel HWIO [3,3,3,16]; stats_ws: 2*b*16 doubles (need not be initialised); out [b,h,w,16], 16-byte aligned. */
+int m4d_rgb_conv_dn(const float* x, int x_pix_stride, const float* kernel_hwio, const float* conv_bias, int b, int h, int w,
+                    const float* dn_scale, const float* dn_bias, float leaky_alpha, double* stats_ws, float* out, void* stream);
 
 /* Keras Conv2D(3x3, padding='same') + bias + optional leaky_relu (:63-72,104-114; TF SAME padding rule).
  * x [b,h,w,cin] with row stride x_pix_stride (>= cin); kernel HWIO [3,3,cin,cout]; y [b,oh,ow,cout] with row

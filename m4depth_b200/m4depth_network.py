@@ -174,13 +174,36 @@ class FeaturePyramid:
         self.conv_layers_s1 = [_Conv2D(n, 1) for n in self.out_sizes]
         self.conv_layers_s2 = [_Conv2D(n, 2) for n in self.out_sizes]
         self.dn_layers = [DomainNormalization(regularizer_weight) for _ in self.out_sizes]   # only [0] is used (:82-83)
+        # conv -> DN as two ops (default) or m4d_rgb_conv_dn, which never stores the conv output but evaluates it twice.
+        # Measured on B200 (config 3): the fused call is 0.18 ms per step SLOWER - the 3->16 conv is instruction-bound
+        # (~400 instructions per pixel), not bound by the 252 MB it writes, so recomputing it costs more than the traffic saved.
+        self.unfused_first_layer = os.environ.get("M4D_FUSED_FIRST_LAYER", "0") != "1"
+
+    def _first_layer_fused(self, conv1, images):
+        dn = self.dn_layers[0]
+        if conv1.kernel is None:
+            raise L.M4DError("conv layer has no weights: call load_weights() first")
+        b, h, w, _ = images.shape
+        if dn.scale is None:
+            dn.build((b, h, w, 16), images.device)
+        key = (b, h, w, 16)
+        ws = dn._ws.get(key)
+        if ws is None:
+            ws = dn._ws[key] = (torch.empty(2 * b * 16, dtype=torch.float64, device=images.device),
+                                torch.empty((b, h, w, 16), dtype=torch.float32, device=images.device))
+        stats, out = ws
+        L.check(L.lib.m4d_rgb_conv_dn(L.ptr(images), _pix_stride(images), L.ptr(conv1.kernel), L.ptr(conv1.bias), b, h, w,
+                                      L.ptr(dn.scale), L.ptr(dn.bias), float(LEAKY), L.ptr(stats), L.ptr(out), L.stream()))
+        return out
 
     def call(self, images):
         L.f32c(images, "images")
         prev_out = images
         out_features = []
         for i, (conv1, conv2) in enumerate(zip(self.conv_layers_s1, self.conv_layers_s2)):
-            if self.use_dinl and i == 0:
+            if self.use_dinl and i == 0 and prev_out.shape[-1] == 3 and conv1.filters == 16 and not self.unfused_first_layer:
+                tmp = self._first_layer_fused(conv1, prev_out)              # conv + DN + leaky_relu, conv output never stored
+            elif self.use_dinl and i == 0:
                 tmp = conv1(prev_out, alpha=1.0)
                 tmp = self.dn_layers[0].call(tmp, leaky_alpha=LEAKY)        # DN then leaky_relu (:83-84)
             else:

@@ -621,6 +621,35 @@ def test_model_loads_reference_format_checkpoint(tmp_path):
     assert torch.equal(outs[0], outs[1]) and torch.isfinite(outs[0]).all()
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 48), (1, 37, 53), (3, 8, 8)])
+def test_first_encoder_layer_fused_conv_dn(shape):
+    """conv3x3(RGB -> 16) + DomainNormalization + leaky_relu in one call that never stores the conv output (both DN passes
+    recompute it) against the oracle and against the two separate ops."""
+    m = _m4d()
+    b, h, w = shape
+    g = torch.Generator().manual_seed(b * h + w)
+    wts = oracle.init_weights(1, seed=9, bias_std=0.05, dn_random=True)
+    rgb = torch.rand(b, h, w, 3, generator=g)
+    conv = oracle.conv2d_same(rgb, wts["encoder/conv_layers_s1/0/kernel"], wts["encoder/conv_layers_s1/0/bias"], 1)
+    dn = oracle.DomainNormalization(wts["encoder/dn_layers/0/scale"], wts["encoder/dn_layers/0/bias"])
+    want = oracle.leaky_relu(dn(conv))
+    settings = {"nbre_lvls": 1, "is_training": False, "ablation": m.M4depthAblationParameters()}
+    outs = []
+    for unfused in (False, True):
+        enc = m.FeaturePyramid(settings)
+        enc.unfused_first_layer = unfused
+        enc.conv_layers_s1[0].assign(wts["encoder/conv_layers_s1/0/kernel"], wts["encoder/conv_layers_s1/0/bias"], "cuda")
+        enc.conv_layers_s2[0].assign(wts["encoder/conv_layers_s2/0/kernel"], wts["encoder/conv_layers_s2/0/bias"], "cuda")
+        enc.dn_layers[0].scale = wts["encoder/dn_layers/0/scale"].cuda().reshape(1, 1, 1, -1).contiguous()
+        enc.dn_layers[0].bias = wts["encoder/dn_layers/0/bias"].cuda().reshape(1, 1, 1, -1).contiguous()
+        x = cu(rgb)
+        tmp = enc._first_layer_fused(enc.conv_layers_s1[0], x) if not unfused else enc.dn_layers[0].call(
+            enc.conv_layers_s1[0](x, alpha=1.0), leaky_alpha=0.1)
+        outs.append(tmp.clone())
+    np.testing.assert_allclose(outs[0].cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
 def test_resize_and_prologue_epilogue_vs_oracle():
     m = _m4d()
     L = m._lib
