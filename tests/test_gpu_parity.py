@@ -580,6 +580,29 @@ def test_conv3x3_tcgen05_3xfp16_vs_oracle(cfg, dyn):
         np.testing.assert_allclose(tc.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
 
 
+@pytest.mark.parametrize("cfg", [(4, 96, 160, 16, 16, 1), (4, 192, 320, 16, 16, 2), (2, 128, 160, 64, 32, 1), (2, 96, 160, 96, 64, 1),
+                                 (2, 96, 160, 64, 128, 1), (3, 96, 128, 32, 5, 1)])
+def test_conv3x3_tcgen05_many_tiles_per_cta(cfg):
+    """Several hundred pixel tiles, i.e. every persistent CTA walks many tiles: the mbarrier rings (halo, weights - streamed or
+    resident -, the two accumulator sets, the alternating epilogue groups of thin layers) wrap around many times."""
+    m = _m4d()
+    b, h, w, cin, cout, stride = cfg
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    pad = (0, 1, 0, 1) if stride == 2 else (1, 1, 1, 1)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.permute(0, 3, 1, 2), pad), k.permute(3, 2, 0, 1), bias, stride=stride)
+    ref = torch.nn.functional.leaky_relu(ref, 0.1).permute(0, 2, 3, 1)
+    from m4depth_b200.m4depth_network import _Conv2D
+    for prec in (1, 0):
+        conv = _Conv2D(cout, stride, prec=prec)
+        conv.assign(k, bias, "cuda")
+        for _ in range(2):                                   # twice: a second launch right behind the first
+            out = conv(cu(x), alpha=0.1, algo=2)
+        np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5 * float(ref.abs().max()))
+
+
 def test_conv3x3_tcgen05_wide_output_split():
     """cout = 192 (> 128 TMEM-friendly columns): output channels sliced over two CTAs per tile, stride 1 (128->192)."""
     m = _m4d()
