@@ -529,7 +529,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int grp = (warp - 8) >> 2, q = warp & 3;
     const int m = q * 32 + lane;
     const int et = threadIdx.x - 256 - grp * 128;                  // 0..127 within the group
-    const uint32_t sbuf = sOut + (uint32_t)grp * OUT_SLOT;
+    // staging tiles for the TMA stores: one per group; with <= 64 output channels group 1 does not store, so group 0 alternates
+    // between both tiles and only waits for the store before the previous one to have read its tile
+    uint32_t nstore = 0;
     const int nchunks = (a.cout + 31) >> 5;
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
@@ -585,7 +587,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
           // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
           // store has finished READING it.
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          const uint32_t sbuf = sOut + (wide_split ? (nstore & 1u) : (uint32_t)grp) * OUT_SLOT;
+          ++nstore;
+          if (et == 0) {
+            if (wide_split) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll

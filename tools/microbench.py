@@ -113,7 +113,8 @@ def conv(b=8):
         algo = int(os.environ.get("CONV_ALGO", "0"))
         if algo == 2 and cv.packed is None:
             algo = 1
-        med, mn = timeit(lambda: cv(x, alpha=0.1, algo=algo), iters=5)
+        force = int(os.environ.get("CONV_FORCE", "0"))          # slices | halo stages << 4 (tuning)
+        med, mn = timeit(lambda: cv(x, alpha=0.1, algo=algo, slices=force), iters=5)
         fl = 2.0 * 9 * ci * co * (-(-h // s)) * (-(-w // s)) * b
         tot += med; totf += fl
         path = "tc" if (algo != 1 and cv.packed is not None and ci >= cv.tc_min_cin) else "ffma"
