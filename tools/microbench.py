@@ -17,7 +17,7 @@ PEAK = 6547.5
 flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
-def timeit(fn, iters=12, flush=True):
+def timeit(fn, iters=12, flush=os.environ.get("NOFLUSH") != "1"):
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
@@ -123,5 +123,6 @@ def conv(b=8):
 
 
 if __name__ == "__main__":
+    nb = int(os.environ.get("B", "8"))
     for a in sys.argv[1:] or ["pscv", "sncv", "conv"]:
-        {"pscv": pscv, "sncv": sncv, "conv": conv}[a]()
+        {"pscv": pscv, "sncv": sncv, "conv": conv}[a](nb)
