@@ -189,6 +189,10 @@ int m4d_conv3x3_tc_fwd_ex(const float* x, int x_pix_stride, const float* packed,
  *   3XFP16  operands scaled by a power of two (per layer for the weights, per pixel tile and 32-channel block for the
  *           activations, from the data) and split into fp16 h1 + 2^-11 h2, kind::f16 MMAs at twice the TF32 rate; the same
  *           three products hi*hi + hi*lo + lo*hi with fp32 accumulation, i.e. the same ~2^-22 relative error class. */
+/* Debug: in libraries built with -DM4D_TC_PROFILE (M4D_NVCC_EXTRA=-DM4D_TC_PROFILE python m4depth_b200/_build.py --force) every
+ * following tensor-core conv launch writes, per CTA, 16 int64 clock64 sums of its warp roles' waits and work into device_buf
+ * ([sm_count][16]; tools/conv_phases.py prints them); NULL switches it off.  Returns 0 in normal builds (no timers compiled in). */
+int m4d_debug_conv_profile(long long* device_buf);
 #define M4D_CONV_PREC_3XTF32 0
 #define M4D_CONV_PREC_3XFP16 1
 int64_t m4d_conv3x3_tc_packed_floats_p(int cin, int cout, int stride, int prec);

@@ -34,7 +34,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", src, "-o", obj]
+            cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("M4D_NVCC_EXTRA", "").split() + ["-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -52,6 +52,7 @@ SIGNATURES = {
     "m4d_conv3x3_tc_pack_s": (_i, [_p, _i, _i, _i, _p, _p]),
     "m4d_conv3x3_tc_fwd_s": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p]),
     "m4d_conv3x3_tc_fwd_ex": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p]),
+    "m4d_debug_conv_profile": (_i, [_p]),
     "m4d_conv3x3_tc_packed_floats_p": (C.c_int64, [_i, _i, _i, _i]),
     "m4d_conv3x3_tc_pack_p": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "m4d_conv3x3_tc_fwd_p": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p]),

@@ -39,6 +39,20 @@ constexpr int MAX_B_STAGES = 32;
 constexpr int OUT_SLOT = 128 * 128;                            // one [128 px][32 ch] fp32 staging tile
 constexpr int NTHREADS = 512;
 
+// Role timing (tools/conv_phases.py): build with -DM4D_TC_PROFILE; every role sums the clocks it spends in each of its waits
+// and in its work and lane 0 writes them to a.prof[blockIdx.x * 16 + slot] at the end.
+#ifdef M4D_TC_PROFILE
+#define PROF_DECL(n) long long prof_##n = 0
+#define PROF_BEGIN(n) const long long prof_t0_##n = clock64()
+#define PROF_END(n) prof_##n += clock64() - prof_t0_##n
+#define PROF_WRITE(slot, n) do { if (a.prof && lane == 0) a.prof[(size_t)blockIdx.x * 16 + (slot)] = prof_##n; } while (0)
+#else
+#define PROF_DECL(n)
+#define PROF_BEGIN(n)
+#define PROF_END(n)
+#define PROF_WRITE(slot, n)
+#endif
+
 struct TcArgs {
   const float* bias;
   float* y;
@@ -56,6 +70,7 @@ struct TcArgs {
   int concat;                       // Cout <= 64: hi*hi and hi*lo in ONE MMA of N = 2*Cout over the adjacent [hi|lo] weight planes
   int s2d_c;                        // 0: stride 1.  C > 0: stride-2 conv over C input channels as a 2x2-cell conv (see below)
   int s2d_chunks;                   // 32-channel chunks of one input row pair's (px, c) range = 2C / 32
+  long long* prof;                  // M4D_TC_PROFILE builds: [grid][16] clock64 sums per role (else unused)
   const float* w_scale;             // 3xFP16 mode: 1 / (power-of-two scale the packed weights were multiplied by), device scalar
   float alpha;
 };
@@ -287,6 +302,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0) {
     // ===== A producer
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    PROF_DECL(a_wait_empty);
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int tile = item / a.nslices;
@@ -294,7 +310,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int s = ka % NA;
-        mbar_wait(a_empty + 8 * s, ((ka / NA) & 1) ^ 1);
+        { PROF_BEGIN(a_wait_empty); mbar_wait(a_empty + 8 * s, ((ka / NA) & 1) ^ 1); PROF_END(a_wait_empty); }
         if (elect_one()) {
           mbar_expect_tx(a_full + 8 * s, A_BYTES);
           if (!S2D) {
@@ -307,6 +323,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         __syncwarp();
       }
     }
+    PROF_WRITE(0, a_wait_empty);
   } else if (warp == 1) {
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -349,18 +366,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // the adjacent [W_hi ; W_lo] planes as one N = 2*Cout operand.  With small N the MMAs are bound by the 4 KB A-operand
     // read from shared memory (128 B/clk), so one A pass less per k-step is 25-30 % of the layer.
     const uint32_t ncol = (uint32_t)a.cout;
+    PROF_DECL(i_wait_acc); PROF_DECL(i_wait_a); PROF_DECL(i_wait_b); PROF_DECL(i_issue);
     int ka = 0, sb = 0, sa = 0;
     uint32_t bph = 0, aph = 0;
     const uint32_t ring_mask = a.b_resident ? 0u : 1u;               // resident weights: every slab's barrier completed phase 0 for good
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       if (a.b_resident) sb = 0;                                      // slab = position within the tile
+      const bool need_wgt_wait = !a.b_resident || item == (int)blockIdx.x;   // resident slabs: landed for good after the first tile
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
         const int set = ka & 1;
-        mbar_wait(acc_empty + 8 * set, ((ka >> 1) & 1) ^ 1);            // epilogue has drained this set
+        { PROF_BEGIN(i_wait_acc); mbar_wait(acc_empty + 8 * set, ((ka >> 1) & 1) ^ 1); PROF_END(i_wait_acc); }   // epilogue has drained this set
+        // orders the MMAs below after the epilogue's tcgen05.ld of this set (its fence::before_thread_sync + arrive).  Once per
+        // k-block: the role timers showed ~700 clocks per fence when it also sat behind every weight-slab wait, where nothing
+        // needs it (TMA writes and the splitters' fence.proxy.async'ed stores reach the tensor core through the mbarriers).
+        tc_fence_after();
         const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
         const uint32_t d_corr = d_set + (CONCAT ? 2u : 1u) * ncol;
-        mbar_wait(a_ready + 8 * sa, aph);
+        { PROF_BEGIN(i_wait_a); mbar_wait(a_ready + 8 * sa, aph); PROF_END(i_wait_a); }
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
         const uint64_t dA_hi = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT, HALO_W * 64) : umma_desc(sA + sa * A_STAGE, HALO_W * 128);
         const uint64_t dA_lo = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT + AH_PLANE, HALO_W * 64)
@@ -375,19 +398,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // fp16 MMAs of a 128-column tap (measured: the issuer, not the tensor pipe, set the pace of every layer).
           int sbs[3];
           {
+            PROF_BEGIN(i_wait_b);
             int s_ = sb;
             uint32_t ph_ = bph;
 #pragma unroll
             for (int j = 0; j < 3; ++j)
               if (j < ntap) {
                 sbs[j] = s_;
-                mbar_wait(b_full + 8 * s_, ph_ & ring_mask);
+                if (need_wgt_wait) mbar_wait(b_full + 8 * s_, ph_ & ring_mask);
                 if (++s_ == NB) { s_ = 0; ph_ ^= 1u; }
               }
             sb = s_;
             bph = ph_;
+            PROF_END(i_wait_b);
           }
-          tc_fence_after();
+          PROF_BEGIN(i_issue);
           if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -429,19 +454,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             }
           }
           __syncwarp();
+          PROF_END(i_issue);
         }
         if (++sa == NA) { sa = 0; aph ^= 1u; }
       }
     }
+    PROF_WRITE(1, i_wait_acc); PROF_WRITE(2, i_wait_a); PROF_WRITE(3, i_wait_b); PROF_WRITE(4, i_issue);
   } else if ((warp >= 4 && warp < 8) || (wide_split && warp >= 12)) {
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
     const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
     const int NS = (int)nsplit;
+    PROF_DECL(s_wait_full); PROF_DECL(s_split);
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int s = ka % NA;
-        mbar_wait(a_full + 8 * s, (ka / NA) & 1);
+        { PROF_BEGIN(s_wait_full); mbar_wait(a_full + 8 * s, (ka / NA) & 1); PROF_END(s_wait_full); }
+        PROF_BEGIN(s_split);
         const uint32_t hi_p = sA + s * A_STAGE, lo_p = hi_p + A_SLOT;
         if (!HALF) {
 #pragma unroll 4
@@ -521,7 +550,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
         mbar_arrive(a_ready + 8 * s);
+        PROF_END(s_split);
       }
+    if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); }
   } else if (warp >= 8 && (!wide_split || warp < 12)) {
     // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant, group g the
     // 32-column chunks g and g+2.  After every k-block the group adds that k-block's accumulators into its register sums and
@@ -533,6 +564,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // between both tiles and only waits for the store before the previous one to have read its tile
     uint32_t nstore = 0;
     const int nchunks = (a.cout + 31) >> 5;
+    PROF_DECL(e_wait_full); PROF_DECL(e_drain); PROF_DECL(e_final);
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int tile = item / a.nslices;
@@ -542,7 +574,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       float sum[2][32];
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int set = ka & 1;
-        mbar_wait(acc_full + 8 * set, (ka >> 1) & 1);
+        { PROF_BEGIN(e_wait_full); mbar_wait(acc_full + 8 * set, (ka >> 1) & 1); PROF_END(e_wait_full); }
+        PROF_BEGIN(e_drain);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
         float inv_main = 1.f;                                       // 3xFP16: 1 / (s_x * s_w) of this k-block, cross terms * 2^-11
@@ -571,7 +604,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty + 8 * set);            // all 8 epilogue warps arrive, with or without chunks
+        PROF_END(e_drain);
       }
+      PROF_BEGIN(e_final);
       const int oy = oy0 + m / TILE_W, ox = ox0 + m % TILE_W;
       const bool valid = oy < a.h && ox < a.w;
       float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
@@ -615,8 +650,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (i < nc && n0 + c0 + i < a.cout_real) yp[n0 + c0 + i] = sum[ci][i];
         }
       }
+      PROF_END(e_final);
     }
     if (a.tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store's reads
+    if (warp == 8) { PROF_WRITE(7, e_wait_full); PROF_WRITE(8, e_drain); PROF_WRITE(9, e_final); }
   }
 
   tc_fence_before();
@@ -722,6 +759,8 @@ EncodeTiledFn get_encode_fn() {
   }();
   return fn;
 }
+
+long long* g_conv_prof = nullptr;      // M4D_TC_PROFILE builds only (m4d_debug_conv_profile)
 
 inline bool tc_shape_ok(int cin, int cout, int stride) {
   if (cin < 1 || cout < 1 || cout > 256) return false;
@@ -836,6 +875,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     my = mw;                                   // unused by the kernel
   }
   TcArgs a;
+  a.prof = g_conv_prof;
   a.bias = bias; a.y = y; a.h = oh; a.w = ow; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha; a.w_scale = w_scale;
   a.s2d_c = stride == 1 ? 0 : cin;
@@ -904,6 +944,16 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
 }  // namespace
 
 extern "C" {
+
+int m4d_debug_conv_profile(long long* device_buf) {
+#ifdef M4D_TC_PROFILE
+  g_conv_prof = device_buf;
+  return 1;
+#else
+  (void)device_buf;
+  return 0;                               // this build carries no role timers
+#endif
+}
 
 int64_t m4d_conv3x3_tc_packed_floats_p(int cin, int cout, int stride, int prec) {
   if (!tc_shape_ok(cin, cout, stride) || (prec != M4D_CONV_PREC_3XTF32 && prec != M4D_CONV_PREC_3XFP16)) return 0;
