@@ -284,7 +284,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(acc_empty + 8 * s, wide_split ? 4 : 8);   // one lane of each epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < MAX_A_STAGES; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
+    for (int i = 0; i < 4; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
   }
   if (warp == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
@@ -465,6 +465,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
     const int NS = (int)nsplit;
     PROF_DECL(s_wait_full); PROF_DECL(s_split);
+    // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
+    const float w_inv_scale = HALF ? __ldg(a.w_scale) : 1.f;
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
       for (int kb = 0; kb < KB; ++kb, ++ka) {
@@ -509,19 +511,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // largest magnitude of the k-block's halo (compared as the bits of |x|: monotonic for finite values)
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-          if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(mx) : "memory");
+          // four slots in rotation: slot (ka & 3) collects this k-block's maximum, slot (ka + 2) & 3 - read two k-blocks ago, not
+          // needed before two k-blocks from now - is cleared, so one barrier per k-block suffices
+          const uint32_t slot = s_max + 4 * (uint32_t)(ka & 3);
+          if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(slot), "r"(mx) : "memory");
           asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory");
           uint32_t mbits;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(s_max + 4 * s) : "memory");
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(slot) : "memory");
           // s_x = 2^(14 - E) with E the exponent of the maximum (so max * s_x is in [2^14, 2^15)); exponents are clamped so that
           // s_x and 1 / s_x are normal floats (all-zero / denormal tiles: any scale gives zeros)
           int E = (int)(mbits >> 23) - 127;
           E = E < -100 ? -100 : (E > 100 ? 100 : E);
           const float sx = __uint_as_float((uint32_t)(127 + 14 - E) << 23);
-          asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory");      // everyone has read the maximum
           if (t == 0) {
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * s), "r"(0u) : "memory");
-            const float inv = __uint_as_float((uint32_t)(127 - 14 + E) << 23) * __ldg(a.w_scale);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * (uint32_t)((ka + 2) & 3)), "r"(0u) : "memory");
+            const float inv = __uint_as_float((uint32_t)(127 - 14 + E) << 23) * w_inv_scale;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_scale + 4 * (ka & 7)), "f"(inv) : "memory");
           }
           const uint32_t h1_p = hi_p + A_SLOT, h2_p = h1_p + AH_PLANE;
