@@ -483,8 +483,12 @@ class M4Depth:
 
     # --------------------------------------------------------------------------------------------- call
     def _forward(self, traj_samples, camera):
-        f_maps_pyrs = [self.encoder(s['RGB_im']) for s in traj_samples]
-        d_maps_pyrs = self.d_estimator(f_maps_pyrs, traj_samples, camera, False)
+        # One frame at a time (the reference encodes all frames first, :358-359): the encoder returns views into per-layer
+        # workspaces that the next call overwrites, so a frame's pyramid must be consumed before the next frame is encoded.
+        # The recurrent state lives in the levels, so this is the same computation.  Only the last frame's maps stay valid.
+        d_maps_pyrs = []
+        for s in traj_samples:
+            d_maps_pyrs += self.d_estimator([self.encoder(s['RGB_im'])], [s], camera, False)
         h, w = traj_samples[-1]['RGB_im'].shape[1:3]
         d1 = d_maps_pyrs[-1][0]["depth"]
         b, ih, iw, _ = d1.shape
@@ -573,3 +577,33 @@ class M4Depth:
     def predict_step(self, data):
         """m4depth_network.py:476-489 for a single frame dict: returns the output dict of call()."""
         return self.call([[data], data["camera"]], training=False)
+
+    def reset_metrics(self):
+        from .metrics import MetricsAccumulator
+        self.compiled_metrics = MetricsAccumulator(self.device)
+
+    def test_step(self, data):
+        """m4depth_network.py:433-474.  ``data``: one sequence element (``depth`` [b,H,W,1]) or a whole sequence (``depth``
+        [b,T,H,W,1], every per-frame entry with the extra axis 1: the KITTI protocol) - then the network runs over the T
+        frames and only the LAST frame is scored, unconditionally (:455-457).  Ground truth is clipped to [0, 80], the estimate
+        to [0.001, 80] (:465-467); a single frame that starts a trajectory (``new_traj``) is not scored (:469).  Returns the
+        running means of the seven metrics (metrics.py), like Keras' ``{m.name: m.result()}``."""
+        if not hasattr(self, "compiled_metrics"):
+            self.reset_metrics()
+        if data["depth"].dim() == 5:
+            seq_len = data["depth"].shape[1]
+            nt_all = data["new_traj"]
+            traj_samples = []
+            for i in range(seq_len):
+                nt = nt_all[:, i] if hasattr(nt_all, "dim") and nt_all.dim() == 2 else nt_all[i]
+                traj_samples.append({"RGB_im": data["RGB_im"][:, i].contiguous(), "rot": data["rot"][:, i].contiguous(),
+                                     "trans": data["trans"][:, i].contiguous(), "new_traj": nt})
+            preds = self.call([traj_samples, data["camera"]], training=False)
+            gt, new_traj = data["depth"][:, -1].contiguous(), False
+        else:
+            preds = self.call([[data], data["camera"]], training=False)
+            gt, nt = data["depth"], data["new_traj"]
+            new_traj = _new_traj_flag(nt)
+        if not new_traj:
+            self.compiled_metrics.update_state(gt.to(self.device), preds["depth"])      # clipping happens in m4d_depth_metrics
+        return self.compiled_metrics.result()

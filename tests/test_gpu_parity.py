@@ -673,6 +673,45 @@ def test_first_encoder_layer_fused_conv_dn(shape):
     np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
+def test_test_step_protocol_single_frames_and_kitti_sequence_mode():
+    """M4Depth.test_step (m4depth_network.py:433-474): per-frame mode skips the frame that starts a trajectory and clips
+    gt / estimate before scoring; sequence mode (5-D inputs) scores only the last frame; both agree with the oracle's
+    metrics on the same depth maps."""
+    m = _m4d()
+    nl, H, W, T = 3, 64, 96, 3
+    wts = oracle.init_weights(nl, seed=6, bias_std=0.05, dn_random=True)
+    g = torch.Generator().manual_seed(12)
+    cam = {"f": torch.tensor([[0.5 * W, 0.5 * H]]).cuda(), "c": torch.tensor([[0.5 * W, 0.5 * H]]).cuda()}
+    rot, trans = motion(g, 1)
+    rgbs = [torch.rand(1, H, W, 3, generator=g) for _ in range(T)]
+    gts = [torch.rand(1, H, W, 1, generator=g) * 100.0 for _ in range(T)]          # some values above the 80 m clip
+    mod = m.M4Depth(nbre_levels=nl, use_cuda_graph=False)
+    mod.load_weights(wts)
+    want = []
+    for t in range(T):
+        data = {"RGB_im": rgbs[t].cuda(), "rot": rot.cuda(), "trans": trans.cuda(), "new_traj": [t == 0], "depth": gts[t].cuda(),
+                "camera": cam}
+        res = mod.test_step(data)
+        if t > 0:
+            want.append(oracle.depth_metrics(gts[t], mod._out.cpu()))
+    assert mod.compiled_metrics.count == T - 1                                     # frame 0 (new_traj) is not scored
+    mean = torch.stack(want).mean(dim=0)                                          # keras Mean of the per-batch values
+    for k, v in zip(oracle.METRIC_NAMES, mean.tolist()):
+        assert abs(res[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, res[k], v)
+    last_single = mod._out.clone()
+    # sequence mode on a fresh model: same frames stacked on axis 1, only the last frame scored
+    mod2 = m.M4Depth(nbre_levels=nl, use_cuda_graph=False)
+    mod2.load_weights(wts)
+    seq = {"RGB_im": torch.stack(rgbs, 1).cuda(), "rot": torch.stack([rot] * T, 1).cuda(), "trans": torch.stack([trans] * T, 1).cuda(),
+           "new_traj": torch.tensor([[True] + [False] * (T - 1)]), "depth": torch.stack(gts, 1).cuda(), "camera": cam}
+    res2 = mod2.test_step(seq)
+    assert mod2.compiled_metrics.count == 1
+    assert torch.equal(mod2._out, last_single)
+    one = oracle.depth_metrics(gts[-1], last_single.cpu())
+    for k, v in zip(oracle.METRIC_NAMES, one.tolist()):
+        assert abs(res2[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, res2[k], v)
+
+
 def test_resize_and_prologue_epilogue_vs_oracle():
     m = _m4d()
     L = m._lib
