@@ -46,6 +46,34 @@ def test_argument_validation_without_gpu():
     assert "multiple of 4" in _lib.last_error()
 
 
+def test_new_entry_points_validate_without_gpu():
+    """The stride-aware tensor-core conv calls, BackProjectGrad, the fused first layer and the SNCV variant selector
+    reject bad arguments with a return code and a message before any device work."""
+    from m4depth_b200 import _lib
+    L = _lib.lib
+    # packed sizes: [kb][tap][2 planes][cout padded to 16][32 channels] (+32 floats for the weight scale), fp16 = half the floats
+    assert L.m4d_conv3x3_tc_packed_floats_p(128, 128, 1, 0) == 4 * 9 * 2 * 128 * 32 + 32
+    assert L.m4d_conv3x3_tc_packed_floats_p(128, 128, 1, 1) == 4 * 9 * 2 * 128 * 16 + 32
+    assert L.m4d_conv3x3_tc_packed_floats_p(16, 5, 1, 1) == 1 * 9 * 2 * 16 * 16 + 32
+    assert L.m4d_conv3x3_tc_packed_floats_p(16, 16, 2, 1) == 2 * 9 * 2 * 16 * 16 + 32          # stride 2: 4C channels in 2 k-blocks
+    assert L.m4d_conv3x3_tc_packed_floats_p(192, 192, 2, 1) == 24 * 9 * 2 * 192 * 16 + 32
+    assert L.m4d_conv3x3_tc_packed_floats_p(24, 16, 2, 1) == 0                                # stride 2 needs cin % 16 == 0
+    assert L.m4d_conv3x3_tc_packed_floats_p(16, 300, 1, 1) == 0 and L.m4d_conv3x3_tc_packed_floats_p(16, 16, 1, 7) == 0
+    assert L.m4d_conv3x3_tc_packed_floats(64, 32) == L.m4d_conv3x3_tc_packed_floats_s(64, 32, 1) == L.m4d_conv3x3_tc_packed_floats_p(64, 32, 1, 0)
+    assert L.m4d_conv3x3_tc_pack_p(None, 16, 16, 1, 1, None, None) == -1 and "null" in _lib.last_error()
+    assert L.m4d_conv3x3_tc_pack_p(16, 24, 16, 2, 1, 16, None) == -1 and "stride" in _lib.last_error()
+    assert L.m4d_conv3x3_tc_fwd_p(16, 16, 16, 16, 1, 8, 8, 16, 16, 1, 5, 0.1, 16, 16, 0, None) == -1 and "precision" in _lib.last_error()
+    assert L.m4d_conv3x3_tc_fwd_p(16, 16, 16, 16, 1, 7, 8, 16, 16, 2, 1, 0.1, 16, 16, 0, None) == -3     # odd height, stride 2: not supported
+    assert "outside the tcgen05 path" in _lib.last_error()
+    assert L.m4d_conv3x3_tc_fwd_p(16, 18, 16, 16, 1, 8, 8, 16, 16, 1, 1, 0.1, 16, 16, 0, None) == -3     # pixel stride not a multiple of 4
+    dim = (ctypes.c_int32 * 6)(1, 4, 4, 1, 1, 0)
+    assert L.m4d_backproject_bwd(16, 16, 16, dim, 16, 16, None) == -1 and "dim[5]" in _lib.last_error()
+    assert L.m4d_backproject_bwd(None, 16, 16, dim, 16, 16, None) == -1 and "null" in _lib.last_error()
+    assert L.m4d_rgb_conv_dn(16, 2, 16, 16, 1, 8, 8, 16, 16, 0.1, 16, 16, None) == -1 and "bad sizes" in _lib.last_error()
+    assert L.m4d_sncv_fwd_ex(16, 16, 1, 4, 4, 8, 1, 2, 16, 25, 0, None) == -1 and "search_range" in _lib.last_error()
+    assert L.m4d_debug_conv_profile(None) in (0, 1)
+
+
 def test_no_cpu_fallback():
     import m4depth_b200
     with pytest.raises(m4depth_b200.M4DError):
