@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Whole-model depth error against the golden vectors (recorded from the reference's Python on tools/tf_shim) for one
-conv configuration; run it under M4D_CONV_ALGO=1 (FFMA2 everywhere), M4D_TC_ACCURATE=1 (4 TMEM accumulators everywhere)
-and with neither (default: 2 accumulators for cout > 64) to see what the convolution's summation error does to the
-depth maps after the fp16 stage of the PSCV has amplified it.  GPU box only."""
+conv configuration: run it under M4D_CONV_ALGO=1 (FFMA2 everywhere), M4D_CONV_PREC=0 (tensor cores, 3xTF32) and with neither
+(default: tensor cores, 3xFP16) to see what the convolution's summation error does to the depth maps after the fp16 stage
+of the PSCV has amplified it (DESIGN.md section 3 quotes the numbers).  GPU box only."""
 import os, sys
 import numpy as np
 import torch
