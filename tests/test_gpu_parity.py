@@ -315,6 +315,35 @@ def test_pscv_edge_cases():
         assert torch.equal(cv.cpu(), want_cv) and torch.equal(pd.cpu(), want_pd)
 
 
+@pytest.mark.parametrize("interp", ["gather", "bp"])
+def test_pscv_degenerate_inputs(interp):
+    """What the reference's arithmetic does with degenerate inputs must come out the same: zero translation (s = 0: 0/0 in the
+    epipolar direction, App. B), NaN / +-Inf / zero parallax at some pixels, a 90-degree rotation, zero features (0/0 in nothing:
+    the PSCV takes normalised features as they are).  NaN patterns and every finite value are compared bit for bit."""
+    m = _m4d()
+    b, h, w, c, cuts = 3, 12, 16, 32, 2
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(77, b, h, w, c, cuts, "kitti")
+    flag = interp == "bp"
+    rot[1] = torch.tensor([0.70710678, 0.0, 0.70710678, 0.0])  # 90 degrees about y: alpha = r_z changes sign across the image
+    pl[2, 0, 1] = float("inf"); pl[2, 0, 2] = float("-inf"); pl[2, 0, 3] = 0.0
+    pt[2, 1, :4] = torch.tensor([float("nan"), float("inf"), 0.0, -1.0]).view(4, 1)
+    c2[2, 5:7] = 0.0
+    if flag:
+        # NaN query points exist only for the BackProject branch (its guard writes zeros).  On the gather branch the reference
+        # itself fails there: floor(NaN) becomes an out-of-range tf.gather index (an error on CPU), so those inputs are not part
+        # of its contract (libm4d returns zeros for them).
+        trans[0] = 0.0                                         # pure rotation: d = 0, s = 0 -> 0/0
+        pl[2, 0, 0] = float("nan")
+    want_cv, want_pd = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, use_cuda_backproject=flag)
+    for kernel_flag in (0, m._lib.INTERP_FLAG_TILE, m._lib.INTERP_FLAG_GENERIC):
+        cv, pd = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4, nbre_cuts=cuts,
+                                                  interp=(m.INTERP_BP if flag else m.INTERP_GATHER) | kernel_flag)
+        for got, want, name in ((cv.cpu(), want_cv, "cv"), (pd.cpu(), want_pd, "prev_disp")):
+            assert torch.equal(torch.isnan(got), torch.isnan(want)), f"{name}: NaN pattern differs (kernel flag {kernel_flag:#x})"
+            ok = ~torch.isnan(want)
+            assert torch.equal(got[ok], want[ok]), f"{name}: finite values differ (kernel flag {kernel_flag:#x})"
+
+
 @pytest.mark.parametrize("shape", LEVEL_SHAPES, ids=[s[0] for s in LEVEL_SHAPES])
 def test_sncv_vs_oracle(shape):
     m = _m4d()
@@ -537,7 +566,8 @@ def test_conv3x3_tcgen05_output_channel_slices(cfg):
 @pytest.mark.parametrize("cfg", [(1, 16, 8, 32, 16, 1), (2, 16, 16, 64, 128, 1), (1, 24, 80, 122, 128, 1), (2, 13, 21, 128, 96, 1),
                                  (1, 6, 20, 470, 128, 1), (1, 33, 47, 96, 64, 1), (1, 12, 40, 238, 32, 1), (1, 20, 9, 16, 16, 1),
                                  (2, 19, 23, 16, 5, 1), (1, 16, 8, 40, 20, 1), (2, 32, 48, 16, 16, 2), (1, 20, 36, 64, 64, 2),
-                                 (1, 12, 40, 192, 192, 2), (1, 34, 18, 48, 80, 2), (1, 12, 40, 128, 192, 1)])
+                                 (1, 12, 40, 192, 192, 2), (1, 34, 18, 48, 80, 2), (1, 12, 40, 128, 192, 1),
+                                 (1, 1, 1, 32, 16, 1), (1, 2, 3, 16, 128, 1), (2, 2, 2, 16, 16, 2), (1, 1, 40, 64, 32, 1)])
 @pytest.mark.parametrize("dyn", ["unit", "wide"])
 def test_conv3x3_tcgen05_3xfp16_vs_oracle(cfg, dyn):
     """The 3xFP16 mode of the tensor-core conv (operands scaled per layer / per tile-k-block and split into fp16 h1 + 2^-11 h2;
