@@ -365,7 +365,7 @@ def run_ours(args, rank, world, local):
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": launches_per_step * K,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": {"kernel": "pscv_kernel (fused backproject + parallax-sweeping cost volume), level 2: 96x320x32, cuts 2, r=4, b=8",
+        "roofline": {"kernel": f"pscv9w_kernel (fused backproject + parallax-sweeping cost volume), level 2: {H // 4}x{W // 4}x32, cuts 2, r=4, b={b}",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": pscv_avg * 1e3,
                      "min_launch_us": pscv_ms[0] * 1e3, "launches_timed": len(pscv_ms), "peak_source": peak_src,
