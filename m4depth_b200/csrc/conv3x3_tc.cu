@@ -928,7 +928,11 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
                                       conv3x3_tc_kernel<true, false, false>,  conv3x3_tc_kernel<true, true, false>,
                                       conv3x3_tc_kernel<false, false, true>,  conv3x3_tc_kernel<false, true, true>,
                                       conv3x3_tc_kernel<true, false, true>,   conv3x3_tc_kernel<true, true, true>};
-  static bool attr_set = false;
+  // function attributes are per device: remember which devices of this process have them
+  static bool attr_set_dev[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     for (int i = 0; i < 8; ++i) {
       cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

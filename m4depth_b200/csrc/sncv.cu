@@ -318,7 +318,11 @@ extern "C" int m4d_sncv_fwd_ex(const float* c1, const float* c2, int b, int h, i
   auto magic = [](int d) { return (0x100000000ull / (unsigned long long)d) + 1ull; };
   a.m_nch = magic(a.gw / 4); a.m_hw = magic(a.TW + 2 * search_range); a.m_tw = magic(a.TW); a.m_oc = magic(n * n * cuts); a.m_tp = magic(TP);
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
+  // function attributes are per device: remember which devices of this process have them
+  static bool attr_set_dev[64] = {};
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  bool& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(sncv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
