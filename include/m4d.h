@@ -122,6 +122,18 @@ int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_pr
                           float* centre_log, int centre_log_pix_stride, float centre_log_scale,
                           int32_t* idx_dbg, int interp, void* stream);
 
+/* Backward of m4d_pscv_fused_fwd in the gather convention (what TensorFlow's autodiff makes of
+ * utils/depth_operations.py:223-281 + utils/dense_image_warp.py:127-190, needed by train_step, m4depth_network.py:371-399):
+ * (d_cv [b,h,w,>=cuts*K], d_prev_disp [b,h,w,>=K] or NULL) -> d_c1 [b,h,w,c] and d_para_prev_l [b,h,w,1] (per-pixel sums,
+ * deterministic), d_c2 [b,h,w,c] and d_para_prev_t [b,h,w,1] (zeroed here, then scatter-added onto the bilinear taps with
+ * floating-point atomics).  The pose and camera get no gradient (they are data).  A parity implementation (one thread per
+ * pixel), not a tuned kernel. */
+int m4d_pscv_fused_bwd(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
+                       const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
+                       int b, int h, int w, int c, int cuts, int search_range,
+                       const float* d_cv, int d_cv_pix_stride, const float* d_prev_disp, int d_pd_pix_stride,
+                       float* d_c1, float* d_c2, float* d_para_prev_t, float* d_para_prev_l, void* stream);
+
 /* ---- L2: spatial self-correlation cost volume ---------------------------------------------------
  * Replaces cost_volume (utils/depth_operations.py:283-313), dilation 1.
  * out[b,y,x,(dy*(2r+1)+dx)*cuts + k] = leaky_0.1(mean_{j in group k} c1[b,y,x,j]*c2pad[b,y+dy-r,x+dx-r,j]) */

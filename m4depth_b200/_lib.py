@@ -39,6 +39,7 @@ SIGNATURES = {
                                 _p, _i, _p, _i, _p, _i, _f, _p, _p]),
     "m4d_pscv_fused_fwd_ex": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                                    _p, _i, _p, _i, _p, _i, _f, _p, _i, _p]),
+    "m4d_pscv_fused_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p]),
     "m4d_sncv_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "m4d_sncv_fwd_ex": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "m4d_group_l2norm": (_i, [_p, _i, _i, _i, _p, _p]),

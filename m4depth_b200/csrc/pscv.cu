@@ -833,6 +833,109 @@ static cudaError_t launch_warp(WArgs& wa, int interp, int ctas_per_sm, cudaStrea
   return e;
 }
 
+// =====================================================================================================================
+// Backward of the fused PSCV (gather convention), for train_step (m4depth_network.py:371-399): what TensorFlow's autodiff
+// makes of utils/depth_operations.py:223-281 + utils/dense_image_warp.py:127-190.  One thread per pixel, serial over the
+// hypotheses and channels (a parity implementation, not a tuned one): d_c1 and d_para_prev_l are thread-private sums
+// (deterministic); d_c2 and d_para_prev_t are scattered onto the four taps with atomics, as BackProjectGrad does.
+// Gradient arithmetic follows the forward's types: cv = fp32(fp16(sum / n)) -> the incoming gradient is rounded to fp16,
+// divided by n in fp32, rounded to fp16 again and multiplied in fp16 with the fp16 operands (:276-277); the warp part is
+// fp32.  floor() and the integer taps carry no gradient; clip ops pass it inside their range (boundaries included).
+struct PscvBwdArgs {
+  PscvArgs a;
+  const float *d_cv, *d_pd;
+  float *d_c1, *d_c2, *d_pt, *d_pl;
+  int dcv_stride, dpd_stride;
+};
+
+__global__ void __launch_bounds__(128) pscv_bwd_kernel(PscvBwdArgs g) {
+  const PscvArgs& a = g.a;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.npix) return;
+  const int H = a.h, W = a.w, C = a.c, K = a.K;
+  const int x = (int)(p % W), y = (int)((p / W) % H), bi = (int)(p / ((int64_t)W * H));
+  Pose P;
+  load_pose(a.rot, a.rot_dim, a.trans, a.cam_f, a.cam_c, bi, P);
+  const Epi e = epipolar(P, x, y);
+  const float para_l = __ldg(a.para_l + p);
+  const int gw = C / a.cuts;
+  const int64_t img = (int64_t)bi * H * W;
+  constexpr int KMAX = 17;
+  int64_t base[KMAX];
+  float ax[KMAX], ay[KMAX], div_[KMAX], rho_[KMAX], dax[KMAX], day[KMAX];
+  bool ok[KMAX], passx[KMAX], passy[KMAX], passr[KMAX];
+  for (int k = 0; k < K; ++k) {
+    const float raw = FADD(para_l, (float)(k - a.r));
+    float rho = (raw != raw) ? raw : fminf(fmaxf(raw, 1e-6f), 1e6f);
+    passr[k] = raw >= 1e-6f && raw <= 1e6f;
+    const float div = FDIV(e.s, rho);
+    const float ex = FDIV(e.dx, div), ey = FDIV(e.dy, div);
+    const float qx = FADD((float)x, FSUB(FADD(e.px, ex), e.sx)), qy = FADD((float)y, FSUB(FADD(e.py, ey), e.sy));
+    ok[k] = qx == qx && qy == qy;
+    const float fx0 = fminf(fmaxf(0.f, floorf(qx)), (float)(W - 2)), fy0 = fminf(fmaxf(0.f, floorf(qy)), (float)(H - 2));
+    const float rx = FSUB(qx, fx0), ry = FSUB(qy, fy0);
+    ax[k] = fminf(fmaxf(rx, 0.f), 1.f);
+    ay[k] = fminf(fmaxf(ry, 0.f), 1.f);
+    passx[k] = rx >= 0.f && rx <= 1.f;
+    passy[k] = ry >= 0.f && ry <= 1.f;
+    base[k] = ok[k] ? img + (int64_t)fy0 * W + (int64_t)fx0 : img;
+    div_[k] = div; rho_[k] = rho;
+    dax[k] = day[k] = 0.f;
+  }
+  // feature channels: d_c1 (private), d_c2 (scatter), d alpha
+  for (int j = 0; j < C; ++j) {
+    const float c1j = __ldg(a.c1 + p * C + j);
+    const __half c1h = __float2half_rn(c1j);
+    const int cut = j / gw;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) {
+      if (!ok[k]) continue;
+      const float gin = __ldg(g.d_cv + p * g.dcv_stride + cut * K + k);
+      const __half gp = __float2half_rn(FDIV(__half2float(__float2half_rn(gin)), (float)gw));
+      const int64_t i00 = base[k] * C + j;
+      const float tl = __ldg(a.c2 + i00), tr = __ldg(a.c2 + i00 + C), bl = __ldg(a.c2 + i00 + (int64_t)W * C), br = __ldg(a.c2 + i00 + (int64_t)(W + 1) * C);
+      const float top = FADD(FMUL(ax[k], FSUB(tr, tl)), tl), bot = FADD(FMUL(ax[k], FSUB(br, bl)), bl);
+      const float sj = FADD(FMUL(ay[k], FSUB(bot, top)), top);
+      acc += __half2float(__hmul(gp, __float2half_rn(sj)));
+      const float ds = __half2float(__hmul(gp, c1h));
+      const float dbot = ds * ay[k], dtop = ds - dbot;
+      const float dtr = dtop * ax[k], dbr = dbot * ax[k];
+      atomicAdd(g.d_c2 + i00, dtop - dtr);
+      atomicAdd(g.d_c2 + i00 + C, dtr);
+      atomicAdd(g.d_c2 + i00 + (int64_t)W * C, dbot - dbr);
+      atomicAdd(g.d_c2 + i00 + (int64_t)(W + 1) * C, dbr);
+      dax[k] += dtop * (tr - tl) + dbot * (br - bl);
+      day[k] += ds * (bot - top);
+    }
+    g.d_c1[p * C + j] = acc;
+  }
+  // the warped previous parallax (prev_disp, :280) and the chain back to the parallax of this level
+  float dpl = 0.f;
+  for (int k = 0; k < K; ++k) {
+    if (!ok[k]) continue;
+    if (g.d_pd != nullptr) {
+      const float ds = __ldg(g.d_pd + p * g.dpd_stride + k);
+      const int64_t i00 = base[k];
+      const float tl = __ldg(a.para_t + i00), tr = __ldg(a.para_t + i00 + 1), bl = __ldg(a.para_t + i00 + W), br = __ldg(a.para_t + i00 + W + 1);
+      const float top = FADD(FMUL(ax[k], FSUB(tr, tl)), tl), bot = FADD(FMUL(ax[k], FSUB(br, bl)), bl);
+      const float dbot = ds * ay[k], dtop = ds - dbot;
+      const float dtr = dtop * ax[k], dbr = dbot * ax[k];
+      atomicAdd(g.d_pt + i00, dtop - dtr);
+      atomicAdd(g.d_pt + i00 + 1, dtr);
+      atomicAdd(g.d_pt + i00 + W, dbot - dbr);
+      atomicAdd(g.d_pt + i00 + W + 1, dbr);
+      dax[k] += dtop * (tr - tl) + dbot * (br - bl);
+      day[k] += ds * (bot - top);
+    }
+    const float dqx = passx[k] ? dax[k] : 0.f, dqy = passy[k] ? day[k] : 0.f;
+    // q = pix + (p_rot + d / div) - start, div = s / rho, rho = clip(para_l + k - r)
+    const float ddiv = -(dqx * e.dx + dqy * e.dy) / (div_[k] * div_[k]);
+    const float drho = -ddiv * e.s / (rho_[k] * rho_[k]);
+    if (passr[k]) dpl += drho;
+  }
+  g.d_pl[p] = dpl;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -956,6 +1059,40 @@ int m4d_pscv_fused_fwd(const float* c1, const float* c2, const float* para_prev_
   return m4d_pscv_fused_fwd_ex(c1, c2, para_prev_t, para_prev_l, rot, rot_dim, trans, cam_f, cam_c, b, h, w, c, cuts,
                                search_range, cv, cv_pix_stride, prev_disp, pd_pix_stride, centre_log,
                                centre_log_pix_stride, centre_log_scale, idx_dbg, M4D_INTERP_GATHER, stream);
+}
+
+int m4d_pscv_fused_bwd(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
+                       const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
+                       int b, int h, int w, int c, int cuts, int search_range,
+                       const float* d_cv, int d_cv_pix_stride, const float* d_prev_disp, int d_pd_pix_stride,
+                       float* d_c1, float* d_c2, float* d_para_prev_t, float* d_para_prev_l, void* stream) {
+  M4D_REQUIRE(c1 && c2 && para_prev_t && para_prev_l && rot && trans && cam_f && cam_c && d_cv && d_c1 && d_c2 && d_para_prev_t &&
+              d_para_prev_l, "m4d_pscv_fused_bwd: null pointer");
+  M4D_REQUIRE(b > 0 && h >= 2 && w >= 2 && c > 0 && cuts > 0, "m4d_pscv_fused_bwd: bad sizes (the gather convention needs h,w >= 2)");
+  M4D_REQUIRE(rot_dim == 3 || rot_dim == 4, "m4d_pscv_fused_bwd: rot_dim must be 3 or 4");
+  M4D_REQUIRE(search_range >= 0 && search_range <= 8, "m4d_pscv_fused_bwd: search_range must be in [0,8] (got %d)", search_range);
+  M4D_REQUIRE(c % cuts == 0, "m4d_pscv_fused_bwd: c must be a multiple of cuts");
+  const int K = 2 * search_range + 1;
+  M4D_REQUIRE(d_cv_pix_stride >= cuts * K && (!d_prev_disp || d_pd_pix_stride >= K), "m4d_pscv_fused_bwd: gradient pixel stride too small");
+  PscvBwdArgs g;
+  PscvArgs& a = g.a;
+  a.c1 = c1; a.c2 = c2; a.para_t = para_prev_t; a.para_l = para_prev_l; a.rot = rot; a.trans = trans; a.cam_f = cam_f; a.cam_c = cam_c;
+  a.cv = nullptr; a.prev_disp = nullptr; a.centre_log = nullptr; a.idx_dbg = nullptr;
+  a.rot_dim = rot_dim; a.b = b; a.h = h; a.w = w; a.c = c; a.cuts = cuts; a.r = search_range; a.K = K; a.Q = 0; a.TP = 0;
+  a.cv_stride = a.pd_stride = a.cl_stride = 0; a.cl_scale = 1.f; a.npix = (int64_t)b * h * w;
+  a.one = 1.0f; a.neg_one = -1.0f; a.neg_zero = -0.0f;
+  g.d_cv = d_cv; g.d_pd = d_prev_disp; g.d_c1 = d_c1; g.d_c2 = d_c2; g.d_pt = d_para_prev_t; g.d_pl = d_para_prev_l;
+  g.dcv_stride = d_cv_pix_stride; g.dpd_stride = d_pd_pix_stride;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(d_c2, 0, (size_t)a.npix * c * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_para_prev_t, 0, (size_t)a.npix * sizeof(float), st);
+  if (e != cudaSuccess) {
+    m4d_set_error("m4d_pscv_fused_bwd: cudaMemsetAsync failed: %s", cudaGetErrorString(e));
+    return M4D_ECUDA;
+  }
+  pscv_bwd_kernel<<<(int)cdiv64(a.npix, 128), 128, 0, st>>>(g);
+  M4D_CHECK_LAUNCH("m4d_pscv_fused_bwd");
+  return M4D_OK;
 }
 
 }  // extern "C"

@@ -90,6 +90,27 @@ def get_parallax_sweeping_cv(c1, c2, disp_prev_t, disp, rot, trans, camera, sear
     return (cv, pd, idx) if return_index_grids else (cv, pd)
 
 
+def get_parallax_sweeping_cv_grad(c1, c2, disp_prev_t, disp, rot, trans, camera, search_range, d_cv, d_prev_disp=None, nbre_cuts=1):
+    """Gradient of ``get_parallax_sweeping_cv`` (gather convention) for given output gradients:
+    -> (d_c1, d_c2, d_disp_prev_t, d_disp).  What TensorFlow's autodiff produces for :223-281 in train_step."""
+    for t, n in ((c1, "c1"), (c2, "c2"), (disp_prev_t, "disp_prev_t"), (disp, "disp"), (d_cv, "d_cv")):
+        L.f32c(t, n)
+    if d_prev_disp is not None:
+        L.f32c(d_prev_disp, "d_prev_disp")
+    rot, trans, f, c = _pose(rot, trans, camera)
+    b, h, w, ch = c1.shape
+    K = 2 * search_range + 1
+    if tuple(d_cv.shape) != (b, h, w, nbre_cuts * K) or (d_prev_disp is not None and tuple(d_prev_disp.shape) != (b, h, w, K)):
+        raise L.M4DError("get_parallax_sweeping_cv_grad: gradient shapes must match the forward outputs")
+    d_c1, d_c2 = torch.empty_like(c1), torch.empty_like(c2)
+    d_pt, d_pl = torch.empty_like(disp_prev_t), torch.empty_like(disp)
+    L.check(L.lib.m4d_pscv_fused_bwd(
+        L.ptr(c1), L.ptr(c2), L.ptr(disp_prev_t), L.ptr(disp), L.ptr(rot), rot.shape[1], L.ptr(trans), L.ptr(f), L.ptr(c),
+        b, h, w, ch, nbre_cuts, search_range, L.ptr(d_cv), nbre_cuts * K, L.ptr(d_prev_disp), K,
+        L.ptr(d_c1), L.ptr(d_c2), L.ptr(d_pt), L.ptr(d_pl), L.stream()))
+    return d_c1, d_c2, d_pt, d_pl
+
+
 def cost_volume(c1, c2, search_range, name="cost_volume", dilation_rate=1, nbre_cuts=1):
     """SNCV (:283-313): [b,h,w,(2r+1)^2*cuts], channel = (dy*(2r+1)+dx)*cuts + cut, leaky_relu(0.1) applied."""
     L.f32c(c1, "c1"), L.f32c(c2, "c2")

@@ -344,6 +344,33 @@ def test_pscv_degenerate_inputs(interp):
             assert torch.equal(got[ok], want[ok]), f"{name}: finite values differ (kernel flag {kernel_flag:#x})"
 
 
+@pytest.mark.parametrize("shape", [(2, 10, 14, 32, 2), (1, 9, 11, 16, 1), (1, 6, 8, 96, 4)])
+def test_pscv_backward_vs_autograd_of_the_oracle(shape):
+    """Backward of the fused PSCV against torch autograd through the oracle's literal forward (the reference's backward IS
+    autodiff of that graph): gradients wrt both feature maps, the previous-frame parallax and this level's parallax.  The
+    fp16 stage makes the gradients fp16-quantised; summation orders differ: 2e-3 of each gradient's scale, and the bulk
+    (99 % of the entries) within 1e-4."""
+    m = _m4d()
+    b, h, w, c, cuts = shape
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(300 + c, b, h, w, c, cuts, "kitti")
+    pl[:, : h // 3] -= 3.0                                                          # some clipped hypotheses (no gradient through the clip)
+    g = torch.Generator().manual_seed(c)
+    d_cv = torch.randn(b, h, w, cuts * 9, generator=g)
+    d_pd = torch.randn(b, h, w, 9, generator=g)
+    leaves = [t.clone().requires_grad_(True) for t in (c1, c2, pt, pl)]
+    cv, pd = oracle.get_parallax_sweeping_cv(leaves[0], leaves[1], leaves[2], leaves[3], rot, trans, cam, 4, nbre_cuts=cuts,
+                                             use_cuda_backproject=False)
+    want = torch.autograd.grad([cv, pd], leaves, [d_cv, d_pd])
+    got = m.utils.get_parallax_sweeping_cv_grad(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4, cu(d_cv), cu(d_pd),
+                                                nbre_cuts=cuts)
+    for name, gg, ww in zip(("d_c1", "d_c2", "d_disp_prev_t", "d_disp"), got, want):
+        gg = gg.cpu()
+        scale = float(ww.abs().max()) + 1e-12
+        err = (gg - ww).abs() / scale
+        assert float(err.max()) <= 2e-3, (name, float(err.max()))
+        assert float(err.flatten().quantile(0.99)) <= 1e-4, (name, float(err.flatten().quantile(0.99)))
+
+
 @pytest.mark.parametrize("shape", LEVEL_SHAPES, ids=[s[0] for s in LEVEL_SHAPES])
 def test_sncv_vs_oracle(shape):
     m = _m4d()

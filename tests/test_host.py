@@ -72,6 +72,10 @@ def test_new_entry_points_validate_without_gpu():
     assert L.m4d_rgb_conv_dn(16, 2, 16, 16, 1, 8, 8, 16, 16, 0.1, 16, 16, None) == -1 and "bad sizes" in _lib.last_error()
     assert L.m4d_sncv_fwd_ex(16, 16, 1, 4, 4, 8, 1, 2, 16, 25, 0, None) == -1 and "search_range" in _lib.last_error()
     assert L.m4d_debug_conv_profile(None) in (0, 1)
+    assert L.m4d_pscv_fused_bwd(16, 16, 16, 16, 16, 4, 16, 16, 16, 1, 1, 8, 32, 2, 4, 16, 18, None, 9, 16, 16, 16, 16, None) == -1
+    assert "h,w >= 2" in _lib.last_error()
+    assert L.m4d_pscv_fused_bwd(16, 16, 16, 16, 16, 4, 16, 16, 16, 1, 8, 8, 32, 2, 4, 16, 17, None, 9, 16, 16, 16, 16, None) == -1
+    assert "stride" in _lib.last_error()
 
 
 def test_no_cpu_fallback():
