@@ -660,6 +660,49 @@ def test_conv3x3_tcgen05_many_tiles_per_cta(cfg):
         np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), rtol=2e-5, atol=2e-5 * float(ref.abs().max()))
 
 
+def test_conv3x3_tcgen05_random_shapes():
+    """Seeded fuzz over the tensor-core conv's shape space: any cin (TMA zero fill of partial k-blocks), cout 1..192 (padding,
+    slices), stride 2 where the cell formulation applies, 1..3 images of 1..70 pixels a side (partial and empty tile rows),
+    both precision modes, inputs inside a wider pixel stride."""
+    m = _m4d()
+    from m4depth_b200.m4depth_network import _Conv2D
+    rng = np.random.default_rng(2024)
+    g = torch.Generator().manual_seed(2024)
+    ran = 0
+    for case in range(48):
+        stride = int(rng.integers(1, 3))
+        cin = int(rng.choice([16, 32, 48, 64, 96, 128, 192])) if stride == 2 else int(rng.integers(16, 260))
+        cout = int(rng.integers(1, 193))
+        if cout > 128 and (-(-cout // 16) * 16) % 64 != 0:
+            cout = 192                                          # beyond 128 channels the slices must be multiples of 32
+        b = int(rng.integers(1, 4))
+        h, w = int(rng.integers(1, 71)), int(rng.integers(1, 71))
+        if stride == 2:
+            h, w = 2 * ((h + 1) // 2), 2 * ((w + 1) // 2)
+        prec = int(rng.integers(0, 2))
+        x = torch.randn(b, h, w, cin, generator=g)
+        k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+        bias = torch.randn(cout, generator=g) * 0.1
+        pad = (0, 1, 0, 1) if stride == 2 else (1, 1, 1, 1)
+        ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), pad), k.double().permute(3, 2, 0, 1),
+                                         bias.double(), stride=stride)
+        ref = torch.nn.functional.leaky_relu(ref, 0.1).permute(0, 2, 3, 1)
+        conv = _Conv2D(cout, stride, prec=prec)
+        conv.assign(k, bias, "cuda")
+        if stride == 1:
+            xs = (cin + 3) // 4 * 4 + 4 * int(rng.integers(0, 2))
+            wide = torch.full((b, h, w, xs), 3.0)
+            wide[..., :cin] = x
+            xin = cu(wide)[..., :cin]
+        else:
+            xin = cu(x)
+        out = conv(xin, alpha=0.1, algo=2)
+        err = float((out.cpu().double() - ref).abs().max()) / (float(ref.abs().max()) + 1e-12)
+        assert err < 5e-6, (case, b, h, w, cin, cout, stride, prec, err)
+        ran += 1
+    assert ran == 48
+
+
 def test_conv3x3_tcgen05_wide_output_split():
     """cout = 192 (> 128 TMEM-friendly columns): output channels sliced over two CTAs per tile, stride 1 (128->192)."""
     m = _m4d()
