@@ -315,6 +315,36 @@ def test_pscv_edge_cases():
         assert torch.equal(cv.cpu(), want_cv) and torch.equal(pd.cpu(), want_pd)
 
 
+def test_pscv_and_sncv_kernels_agree_on_random_shapes():
+    """Seeded fuzz: on 40 random image sizes (partial 8x4 warp tiles, partial 16x8 super tiles, images smaller than a tile)
+    and the network's (c, cuts) pairs the specialised PSCV kernels equal the shape-generic one bit for bit (cv, prev_disp, tap
+    grids), and the column-strip SNCV kernel equals the (pixel, dy) kernel."""
+    m = _m4d()
+    L = m._lib
+    rng = np.random.default_rng(7)
+    pairs = [(16, 1), (32, 2), (64, 2), (96, 4), (128, 4), (192, 8)]
+    for case in range(40):
+        c, cuts = pairs[int(rng.integers(0, len(pairs)))]
+        b, h, w = int(rng.integers(1, 4)), int(rng.integers(2, 45)), int(rng.integers(2, 70))
+        interp = int(rng.integers(0, 3))
+        c1, c2, pt, pl, rot, trans, cam = pscv_inputs(1000 + case, b, h, w, c, cuts, ["kitti", "midair", "tartan"][case % 3])
+        args = [cu(t) for t in (c1, c2, pt, pl, rot, trans)]
+        dc = dev_cam(cam)
+        ref = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=interp | L.INTERP_FLAG_GENERIC, return_index_grids=True)
+        got = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=interp, return_index_grids=True)
+        for a_, b_ in zip(got, ref):
+            assert torch.equal(a_.view(torch.int32) if a_.dtype == torch.float32 else a_,
+                               b_.view(torch.int32) if b_.dtype == torch.float32 else b_), (case, b, h, w, c, cuts, interp)
+        if cuts <= 4:
+            oc = 49 * cuts
+            outs = []
+            for variant in (2, 1):
+                o = torch.empty(b, h, w, oc, device="cuda")
+                L.check(L.lib.m4d_sncv_fwd_ex(L.ptr(args[0]), L.ptr(args[1]), b, h, w, c, cuts, 3, L.ptr(o), oc, variant, L.stream()))
+                outs.append(o)
+            assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)), (case, b, h, w, c, cuts)
+
+
 @pytest.mark.parametrize("interp", ["gather", "bp"])
 def test_pscv_degenerate_inputs(interp):
     """What the reference's arithmetic does with degenerate inputs must come out the same: zero translation (s = 0: 0/0 in the
