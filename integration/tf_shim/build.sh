@@ -17,4 +17,4 @@ mkdir -p "$OUT"
 g++ -std=c++17 -shared -fPIC -O2 "$HERE/m4d_tf_ops.cc" -o "$OUT/backproject.so" \
     "${TF_CFLAGS[@]}" -DGOOGLE_CUDA=1 -I/usr/local/cuda/include \
     -L"$ROOT/m4depth_b200" -l:libm4d.so -Wl,-rpath,"$ROOT/m4depth_b200" "${TF_LFLAGS[@]}"
-echo "wrote $OUT/backproject.so (ops: BackProject, BackProjectGrad, M4dPscvFused, M4dSncv)"
+echo "wrote $OUT/backproject.so (ops: BackProject, BackProjectGrad, M4dPscvFused, M4dPscvFusedGrad, M4dSncv)"

@@ -4,7 +4,7 @@
 // GPU box, so this file is compiled only by integration/tf_shim/build.sh on a machine that has TF 2.x.  It exists so that
 // a maintainer of the reference can keep `utils/dense_image_warp.py:36-52` byte for byte: the shared object registers the
 // SAME op names ("BackProject", "BackProjectGrad": cuda_backproject/backproject_op.cc:32-42,163-164) and forwards them to
-// m4d_backproject_fwd / m4d_backproject_bwd, plus two fused ops for the hot path (M4dPscvFused, M4dSncv) that replace
+// m4d_backproject_fwd / m4d_backproject_bwd, plus fused ops for the hot path (M4dPscvFused + its gradient, M4dSncv) that replace
 // utils/depth_operations.py:223-281 and :283-313.  No arithmetic lives here: shapes, allocation, stream, error mapping.
 //
 // Differences from the reference's op library, on purpose:
@@ -152,6 +152,59 @@ class M4dPscvFused : public OpKernel {
   int r_, cuts_, interp_;
 };
 REGISTER_KERNEL_BUILDER(Name("M4dPscvFused").Device(DEVICE_GPU), M4dPscvFused);
+
+// Gradient op of M4dPscvFused (gather convention), to be registered from Python:
+//   @ops.RegisterGradient("M4dPscvFused")
+//   def _pscv_grad(op, d_cv, d_prev_disp):
+//       g = _m4d_ops.m4d_pscv_fused_grad(*op.inputs, d_cv, d_prev_disp, search_range=op.get_attr("search_range"),
+//                                        nbre_cuts=op.get_attr("nbre_cuts"))
+//       return [g.d_c1, g.d_c2, g.d_disp_prev_t, g.d_disp, None, None, None, None]      # pose and camera are data
+REGISTER_OP("M4dPscvFusedGrad")
+    .Input("c1: float32")
+    .Input("c2: float32")
+    .Input("disp_prev_t: float32")
+    .Input("disp: float32")
+    .Input("rot: float32")
+    .Input("trans: float32")
+    .Input("cam_f: float32")
+    .Input("cam_c: float32")
+    .Input("d_cv: float32")
+    .Input("d_prev_disp: float32")
+    .Attr("search_range: int = 4")
+    .Attr("nbre_cuts: int = 1")
+    .Output("d_c1: float32")
+    .Output("d_c2: float32")
+    .Output("d_disp_prev_t: float32")
+    .Output("d_disp: float32")
+    .SetShapeFn([](shape_inference::InferenceContext* c) {
+      for (int i = 0; i < 4; ++i) c->set_output(i, c->input(i));
+      return Status();
+    });
+
+class M4dPscvFusedGrad : public OpKernel {
+ public:
+  explicit M4dPscvFusedGrad(OpKernelConstruction* c) : OpKernel(c) {
+    OP_REQUIRES_OK(c, c->GetAttr("search_range", &r_));
+    OP_REQUIRES_OK(c, c->GetAttr("nbre_cuts", &cuts_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& c1 = ctx->input(0);
+    OP_REQUIRES(ctx, c1.dims() == 4 && ctx->input(1).shape() == c1.shape(), errors::InvalidArgument("M4dPscvFusedGrad: c1/c2 must be [b,h,w,c]"));
+    const int b = c1.dim_size(0), h = c1.dim_size(1), w = c1.dim_size(2), c = c1.dim_size(3), K = 2 * r_ + 1;
+    const Tensor& rot = ctx->input(4);
+    Tensor* out[4];
+    for (int i = 0; i < 4; ++i) OP_REQUIRES_OK(ctx, ctx->allocate_output(i, ctx->input(i).shape(), &out[i]));
+    if (c1.NumElements() == 0) return;
+    auto p = [&](int i) { return ctx->input(i).flat<float>().data(); };
+    M4D_TF_CHECK(ctx, m4d_pscv_fused_bwd(p(0), p(1), p(2), p(3), p(4), (int)rot.dim_size(1), p(5), p(6), p(7), b, h, w, c, cuts_, r_, p(8),
+                                         cuts_ * K, p(9), K, out[0]->flat<float>().data(), out[1]->flat<float>().data(),
+                                         out[2]->flat<float>().data(), out[3]->flat<float>().data(), stream_of(ctx)));
+  }
+
+ private:
+  int r_, cuts_;
+};
+REGISTER_KERNEL_BUILDER(Name("M4dPscvFusedGrad").Device(DEVICE_GPU), M4dPscvFusedGrad);
 
 // ------------------------------------------------------------------------------------------------ SNCV
 // out = cost_volume(c1, c2, search_range, nbre_cuts=nbre_cuts)   (leaky_relu(0.1) included, utils/depth_operations.py:311)
