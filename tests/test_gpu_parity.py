@@ -931,6 +931,31 @@ def test_pscv_headline_size_vs_oracle_and_batch_independence():
         assert torch.equal(cvi[0], cv[i]) and torch.equal(pdi[0], pd[i])
 
 
+def test_model_shapes_are_static_like_the_reference_state_variables():
+    """The levels' recurrent state is allocated for one (batch, height, width), as the reference's tf.Variables are
+    (m4depth_network.py:160-163): a later call with another shape is refused with an error, not silently re-built; a second
+    model object handles the other shape."""
+    m = _m4d()
+    nl = 4
+    wts = oracle.init_weights(nl, seed=8, bias_std=0.05, dn_random=True)
+
+    def frame(b, H, W, t, g):
+        rot, trans = motion(g, b)
+        return {"RGB_im": cu(torch.rand(b, H, W, 3, generator=g)), "rot": cu(rot), "trans": cu(trans), "new_traj": [t == 0] * b}
+
+    g = torch.Generator().manual_seed(1)
+    model = m.M4Depth(nbre_levels=nl, use_cuda_graph=True)
+    model.load_weights(wts)
+    for t in range(3):
+        model([[frame(2, 64, 96, t, g)], dev_cam(camera_for("kitti", 2, 64, 96))])
+    with pytest.raises(m.M4DError, match="static shapes"):
+        model([[frame(1, 96, 64, 0, g)], dev_cam(camera_for("kitti", 1, 96, 64))])
+    other = m.M4Depth(nbre_levels=nl, use_cuda_graph=True)
+    other.load_weights(wts)
+    out = other([[frame(1, 96, 64, 0, g)], dev_cam(camera_for("kitti", 1, 96, 64))])["depth"]
+    assert tuple(out.shape) == (1, 96, 64, 1) and float(out.min()) == 1000.0
+
+
 def test_model_streaming_graph_equals_eager():
     """6 levels, 5 frames with a trajectory reset in the middle: CUDA-graph replay is bit-identical to eager execution."""
     m = _m4d()
