@@ -7,8 +7,9 @@
   ``inputs [B,H,W,F,C]``, ``coords [B,H,W,S,F,2]`` (x,y) signature of ``backproject_op.cc:32-35,53-92``.
 * ``dense_image_warp``      restates ``dense_image_warp.py:195-268`` and dispatches to either.
 
-A plain-C restatement of the BackProject kernel body lives in ``oracle/m4d_oracle.c`` and is
-cross-checked against ``back_project`` in tests.
+A plain-C restatement of the BackProject kernel bodies (forward and gradient) lives in ``oracle/m4d_oracle.c``
+(built by ``oracle/Makefile``) and is cross-checked against ``back_project`` / ``back_project_grad`` in
+``tests/test_oracle_golden.py``.
 """
 import torch
 

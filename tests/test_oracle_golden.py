@@ -147,3 +147,35 @@ def test_back_project_grad_restatement_matches_autograd_of_the_forward():
     np.testing.assert_allclose(cg.numpy(), c64.grad.numpy(), rtol=1e-4, atol=1e-4)
     # and the forward used for the autograd check is the oracle's forward
     np.testing.assert_allclose(oracle.back_project(inp, coords).numpy(), fwd64(inp.double(), coords.double()).detach().numpy(), atol=1e-5)
+
+
+def test_plain_c_restatement_of_the_backproject_kernels_agrees_with_the_torch_oracle():
+    """oracle/m4d_oracle.c restates the reference's two BackProject kernel bodies (backproject_op_gpu.cu.cc:19-79, 108-196)
+    as plain C; the torch oracle must agree with it: forward and tap grids bit for bit (same expression, separately rounded),
+    the gradients to summation-order tolerance."""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "-C", os.path.join(root, "oracle")], check=True)
+    lib = ctypes.CDLL(os.path.join(root, "oracle", "libm4d_oracle.so"))
+    g = torch.Generator().manual_seed(17)
+    B, H, W, S, Fd, C = 2, 7, 9, 3, 2, 5
+    inp = torch.randn(B, H, W, Fd, C, generator=g)
+    coords = torch.rand(B, H, W, S, Fd, 2, generator=g) * torch.tensor([W + 2.0, H + 2.0]) - 1.0
+    coords[0, 0, 0, 0, 0, 0] = float("nan")
+    coords[0, 1, 1, 0, 0] = torch.tensor([3.0, 2.0])
+    coords[1, 2, 2, 1, 1] = torch.tensor([W - 1.0, H - 1.0])
+    grad = torch.randn(B, H, W, S, Fd, C, generator=g)
+    dim = (ctypes.c_int32 * 6)(B, H, W, S, Fd, C)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    out = torch.empty(B, H, W, S, Fd, C)
+    idx = torch.empty(B, H, W, S, Fd, 4, dtype=torch.int32)
+    lib.bp_forward(ptr(inp), ptr(coords), dim, ptr(out), ptr(idx))
+    assert torch.equal(out, oracle.back_project(inp, coords))
+    x0, x1, y0, y1, _ = oracle.back_project_index_grids(coords, H, W)
+    assert torch.equal(idx, torch.stack((x0, x1, y0, y1), dim=-1))
+    ig, cg = torch.empty_like(inp), torch.empty_like(coords)
+    lib.bp_backward(ptr(grad), ptr(inp), ptr(coords), dim, ptr(ig), ptr(cg))
+    want_i, want_c = oracle.back_project_grad(inp, coords, grad)
+    np.testing.assert_allclose(ig.numpy(), want_i.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(cg.numpy(), want_c.numpy(), rtol=1e-5, atol=1e-5)
