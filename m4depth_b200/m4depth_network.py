@@ -575,8 +575,9 @@ class M4Depth:
     __call__ = call
 
     def predict_step(self, data):
-        """m4depth_network.py:476-489 for a single frame dict: returns the output dict of call()."""
-        return self.call([[data], data["camera"]], training=False)
+        """m4depth_network.py:476-489 for a single frame dict: {"image", "depth", "new_traj"} like the reference."""
+        preds = self.call([[data], data["camera"]], training=False)
+        return {"image": data["RGB_im"], "depth": preds["depth"], "new_traj": data["new_traj"]}
 
     def reset_metrics(self):
         from .metrics import MetricsAccumulator

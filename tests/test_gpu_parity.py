@@ -825,6 +825,10 @@ def test_test_step_protocol_single_frames_and_kitti_sequence_mode():
         if t > 0:
             want.append(oracle.depth_metrics(gts[t], mod._out.cpu()))
     assert mod.compiled_metrics.count == T - 1                                     # frame 0 (new_traj) is not scored
+    pred = mod.predict_step({"RGB_im": rgbs[0].cuda(), "rot": rot.cuda(), "trans": trans.cuda(), "new_traj": [True], "camera": cam})
+    assert sorted(pred) == ["depth", "image", "new_traj"] and tuple(pred["depth"].shape) == (1, H, W, 1)      # :481-488
+    mod.predict_step({"RGB_im": rgbs[1].cuda(), "rot": rot.cuda(), "trans": trans.cuda(), "new_traj": [False], "camera": cam})
+    mod.predict_step({"RGB_im": rgbs[2].cuda(), "rot": rot.cuda(), "trans": trans.cuda(), "new_traj": [False], "camera": cam})
     mean = torch.stack(want).mean(dim=0)                                          # keras Mean of the per-batch values
     for k, v in zip(oracle.METRIC_NAMES, mean.tolist()):
         assert abs(res[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, res[k], v)
