@@ -935,6 +935,45 @@ def test_pscv_headline_size_vs_oracle_and_batch_independence():
         assert torch.equal(cvi[0], cv[i]) and torch.equal(pdi[0], pd[i])
 
 
+@pytest.mark.parametrize("off", ["DINL", "SNCV", "time_recurr", "normalize_features", "subdivide_features", "level_memory"])
+def test_model_ablations_vs_oracle(off):
+    """M4depthAblationParameters (m4depth_network.py:21-22): each switch turned off in turn changes the refiner input layout
+    / the feature preparation / the encoder; the whole model must still follow the oracle model built with the same settings."""
+    m = _m4d()
+    nl, b, H, W = 3, 1, 64, 96
+    flags = dict(DINL=True, SNCV=True, time_recurr=True, normalize_features=True, subdivide_features=True, level_memory=True)
+    flags[off] = False
+    ab_ref = oracle.M4depthAblationParameters(**flags)
+    ab_gpu = m.M4depthAblationParameters(**flags)
+    # the refiner input width depends on the switches (m4depth_network.py:223-242): first refiner kernel of every level to match
+    wts = oracle.init_weights(nl, seed=11, bias_std=0.05, dn_random=True)
+    cuts = lambda lvl: (2 ** (lvl // 2)) if flags["subdivide_features"] else 1
+    for lvl in range(1, nl + 1):
+        cin = 9 * cuts(lvl) + 1 + (4 if flags["level_memory"] else 0) + (49 * cuts(lvl) if flags["SNCV"] else 0) + (1 if flags["time_recurr"] else 0)
+        gk = torch.Generator().manual_seed(100 + lvl)
+        wts[f"d_estimator/levels/{lvl - 1}/disp_refiner/prep_conv_layers/0/kernel"] = torch.randn(3, 3, cin, 128, generator=gk) * (2.0 / (9 * cin)) ** 0.5
+    ref = oracle.M4Depth(wts, nbre_levels=nl, ablation_settings=ab_ref, pscv_kwargs={"use_cuda_backproject": False})
+    mod = m.M4Depth(nbre_levels=nl, ablation_settings=ab_gpu, use_cuda_graph=False)
+    mod.load_weights(wts)
+    g = torch.Generator().manual_seed(31)
+    cam = camera_for("kitti", b, H, W)
+    for t in range(3):
+        rot, trans = motion(g, b)
+        rgb = torch.rand(b, H, W, 3, generator=g)
+        s = {"RGB_im": rgb, "rot": rot, "trans": trans, "new_traj": [t == 0] * b}
+        want = ref([[s], cam])["depth"].numpy()
+        got = mod([[{k: (cu(v) if hasattr(v, "shape") else v) for k, v in s.items()}], dev_cam(cam)])["depth"].cpu().numpy()
+        # A mis-wired layout (wrong channel offsets, a missing input) shows as O(0.1-1) errors everywhere.  The bound is looser
+        # than check_depth's: without DN / feature normalisation the fp16 stage of the PSCV sees unnormalised magnitudes and
+        # amplifies the legitimate 1e-7 summation-order differences more (measured: median <= 9e-5, 99th percentile <= 5e-3).
+        err = np.abs(got - want) / (np.abs(want) + 0.1)
+        if t == 0:
+            assert err.max() <= 1e-4
+        else:
+            assert np.median(err) <= 5e-4 and np.percentile(err, 99) <= 2e-2 and err.max() <= 0.2, \
+                (off, t, np.median(err), np.percentile(err, 99), err.max())
+
+
 def test_model_shapes_are_static_like_the_reference_state_variables():
     """The levels' recurrent state is allocated for one (batch, height, width), as the reference's tf.Variables are
     (m4depth_network.py:160-163): a later call with another shape is refused with an error, not silently re-built; a second
