@@ -115,12 +115,20 @@ int m4d_pscv_fused_fwd(const float* c1, const float* c2, const float* para_prev_
  * (c, cuts) pairs) would run.  Same results bit for bit.  Bits 12-15, when non-zero, override the resident CTAs per SM
  * of the persistent grid (tuning experiments only). */
 #define M4D_INTERP_FLAG_TILE 0x200
+/* OR-ed into interp: use the warp-autonomous LDG-gather kernel (pscv9w_kernel) where the shared-memory staged one
+ * (pscv9s_kernel: gather convention, c = 32 / cuts = 2) would run.  Same results bit for bit. */
+#define M4D_INTERP_FLAG_WARP 0x400
 int m4d_pscv_fused_fwd_ex(const float* c1, const float* c2, const float* para_prev_t, const float* para_prev_l,
                           const float* rot, int rot_dim, const float* trans, const float* cam_f, const float* cam_c,
                           int b, int h, int w, int c, int cuts, int search_range,
                           float* cv, int cv_pix_stride, float* prev_disp, int pd_pix_stride,
                           float* centre_log, int centre_log_pix_stride, float centre_log_scale,
                           int32_t* idx_dbg, int interp, void* stream);
+
+/* Debug / test hook: the branch-free IEEE division of the shared-memory staged PSCV kernel (csrc/pscv_smem.cu, phase 0) next
+ * to __fdiv_rn on n operand pairs; unsafe_flag[i] = 1 where the kernel would fall back to __fdiv_rn.  Tests require
+ * out_fast == out_ieee bit for bit wherever the flag is 0. */
+int m4d_debug_div_check(const float* a, const float* b, int n, float* out_fast, float* out_ieee, int32_t* unsafe_flag, void* stream);
 
 /* Backward of m4d_pscv_fused_fwd in the gather convention (what TensorFlow's autodiff makes of
  * utils/depth_operations.py:223-281 + utils/dense_image_warp.py:127-190, needed by train_step, m4depth_network.py:371-399):

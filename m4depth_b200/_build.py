@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libm4d.so")
-SOURCES = ["capi.cu", "elementwise.cu", "pscv.cu", "sncv.cu", "conv3x3.cu", "conv3x3_tc.cu"]
+SOURCES = ["capi.cu", "elementwise.cu", "pscv.cu", "pscv_smem.cu", "sncv.cu", "conv3x3.cu", "conv3x3_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 
@@ -24,7 +24,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "m4d.h")]
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cuh")] + [os.path.join(HERE, "..", "include", "m4d.h")]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs = []
@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["--cudart", "static"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["--cudart", "static", "-Xlinker", "--no-undefined"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -39,6 +39,7 @@ SIGNATURES = {
                                 _p, _i, _p, _i, _p, _i, _f, _p, _p]),
     "m4d_pscv_fused_fwd_ex": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i,
                                    _p, _i, _p, _i, _p, _i, _f, _p, _i, _p]),
+    "m4d_debug_div_check": (_i, [_p, _p, _i, _p, _p, _p, _p]),
     "m4d_pscv_fused_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p]),
     "m4d_sncv_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "m4d_sncv_fwd_ex": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
@@ -77,6 +78,7 @@ ABI_VERSION = lib.m4d_abi_version()
 INTERP_GATHER, INTERP_BP, INTERP_BP_FMA = 0, 1, 2
 INTERP_FLAG_GENERIC = 0x100     # OR into interp: shape-generic PSCV kernel instead of the specialised one
 INTERP_FLAG_TILE = 0x200        # OR into interp: CTA-tile K=9 kernel instead of the warp-autonomous one
+INTERP_FLAG_WARP = 0x400        # OR into interp: warp-autonomous LDG-gather kernel instead of the shared-memory staged one
 
 
 class M4DError(RuntimeError):

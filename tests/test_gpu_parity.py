@@ -345,6 +345,95 @@ def test_pscv_and_sncv_kernels_agree_on_random_shapes():
             assert torch.equal(outs[0].view(torch.int32), outs[1].view(torch.int32)), (case, b, h, w, c, cuts)
 
 
+def test_fast_division_is_ieee():
+    """Phase 0 of pscv9s_kernel divides with MUFU.RCP + five FFMA and no branch (csrc/pscv_smem.cu div_fast): wherever it does
+    not flag its operands as unsafe the quotient must be the IEEE round-to-nearest one, bit for bit - random mantissas over
+    the whole safe exponent range, operands straddling the range limits, exact and near-exact quotients, the values the
+    geometry produces (s / 1e-6, d / 1e8, small integers)."""
+    m = _m4d()
+    L = m._lib
+    g = torch.Generator().manual_seed(11)
+    n = 1 << 22
+    def rnd(lo, hi):
+        mant = 1.0 + torch.rand(n, generator=g, dtype=torch.float64)
+        e = torch.randint(lo, hi + 1, (n,), generator=g).to(torch.float64)
+        sgn = torch.where(torch.rand(n, generator=g) < 0.5, -1.0, 1.0).to(torch.float64)
+        return (sgn * mant * torch.pow(torch.tensor(2.0, dtype=torch.float64), e)).to(torch.float32)
+    cases = [(rnd(-60, 59), rnd(-60, 59)), (rnd(-70, 70), rnd(-70, 70)), (rnd(-20, 20), rnd(-2, 2)),
+             (rnd(-126, 127), rnd(-126, 127))]
+    k = torch.arange(1, n + 1, dtype=torch.float32)
+    cases.append((k, torch.full((n,), 3.0)))
+    cases.append((torch.rand(n, generator=g) * 300.0 + 1e-3, torch.full((n,), 1e-6)))
+    cases.append((torch.randn(n, generator=g) * 200.0, torch.rand(n, generator=g) * 3e8 + 1e6))
+    special = torch.tensor([0.0, -0.0, float("inf"), float("nan"), 1e-45, 1.17549435e-38, 3.4e38, 1.0, 2.0 ** -60, 2.0 ** 60,
+                            2.0 ** -61, 2.0 ** 61])
+    cases.append((special.repeat_interleave(len(special)), special.repeat(len(special))))
+    safe_total = 0
+    for a, b in cases:
+        a, b = a.cuda().contiguous(), b.cuda().contiguous()
+        nn = a.numel()
+        qf, qi = torch.empty(nn, device="cuda"), torch.empty(nn, device="cuda")
+        fl = torch.empty(nn, dtype=torch.int32, device="cuda")
+        L.check(L.lib.m4d_debug_div_check(L.ptr(a), L.ptr(b), nn, L.ptr(qf), L.ptr(qi), L.ptr(fl), L.stream()))
+        safe = fl == 0
+        assert torch.equal(qf[safe].view(torch.int32), qi[safe].view(torch.int32))
+        # the IEEE reference itself: fp64 quotient rounded once to fp32 (exact for fp32 operands up to double rounding, which
+        # cannot occur for a 24-bit by 24-bit quotient in 53 bits)
+        want = (a.double() / b.double()).float()
+        ok = safe & torch.isfinite(want) & (want.abs() > 1e-37)
+        assert torch.equal(qi[ok].view(torch.int32), want[ok].view(torch.int32))
+        ea, eb = (a.view(torch.int32) >> 23) & 0xFF, (b.view(torch.int32) >> 23) & 0xFF
+        inrange = (ea >= 67) & (ea <= 187) & (eb >= 67) & (eb <= 187)
+        assert torch.equal(safe, inrange)
+        safe_total += int(safe.sum())
+    assert safe_total > 4 * n
+
+
+@pytest.mark.parametrize("shape", [(8, 96, 320), (2, 96, 96), (3, 37, 53), (1, 120, 160), (2, 9, 17), (1, 2, 2)])
+@pytest.mark.parametrize("data", ["micro", "insitu", "far", "nan"])
+def test_pscv_smem_staged_kernel_equals_ldg_kernels(shape, data):
+    """pscv9s_kernel (c2 window staged in shared memory by bulk copies, csrc/pscv_smem.cu) against the warp-autonomous LDG
+    kernel and, at small sizes, the shape-generic one: cv, prev_disp, the integer tap grids and the fused log(centre) output
+    bit for bit.  Data: the microbench distribution (boxes of 300-800 pixels), in-situ-like small parallax (3-4 of the 9
+    hypotheses collapse onto one point: the duplicate-record skip), parallax far beyond the window (tiles that overflow
+    the window buffer take the LDG taps inside the same kernel; taps clamped at the image border), NaN / Inf parallax
+    (records without taps, tiles without any tap)."""
+    m = _m4d()
+    L = m._lib
+    b, h, w = shape
+    c, cuts = 32, 2
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(500 + h + w, b, h, w, c, cuts, "kitti")
+    g = torch.Generator().manual_seed(h * w)
+    if data == "insitu":
+        pl = 0.6 + 1.7 * torch.rand(b, h, w, 1, generator=g)
+    elif data == "far":
+        pl = pl * torch.where(torch.rand(b, h, w, 1, generator=g) < 0.02, 30.0, 1.0)
+        pl[:, : max(1, h // 4)] *= -1.0
+    elif data == "nan":
+        pl[0, : min(h, 17)] = float("nan")
+        pl[-1, -1, -1] = float("inf")
+        pl[torch.rand(b, h, w, 1, generator=g) < 0.05] = float("nan")
+    args = [cu(x) for x in (c1, c2, pt, pl, rot, trans)]
+    dc = dev_cam(cam)
+    flags = (0, L.INTERP_FLAG_WARP) + ((L.INTERP_FLAG_GENERIC,) if b * h * w <= 20000 else ())
+    res = []
+    for flag in flags:
+        cv, pd, idx = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=flag, return_index_grids=True)
+        xs = 124
+        wide = torch.full((b, h, w, xs), -7.0, device="cuda")
+        L.check(L.lib.m4d_pscv_fused_fwd_ex(
+            L.ptr(args[0]), L.ptr(args[1]), L.ptr(args[2]), L.ptr(args[3]), L.ptr(args[4]), 4, L.ptr(args[5]), L.ptr(dc["f"]),
+            L.ptr(dc["c"]), b, h, w, c, cuts, 4, wide.data_ptr(), xs, None, 0, wide.data_ptr() + 4 * 121, xs, 0.5,
+            None, flag, L.stream()))
+        res.append((cv.cpu(), pd.cpu(), idx.cpu(), wide.cpu()))
+    bits = lambda t: t.view(torch.int32) if t.dtype == torch.float32 else t
+    for other in res[1:]:
+        for a_, b_ in zip(res[0], other):
+            assert torch.equal(bits(a_), bits(b_))
+    cv, _, _, wide = res[0]
+    assert torch.equal(bits(wide[..., :18]), bits(cv)) and torch.all(wide[..., 18:121] == -7.0) and torch.all(wide[..., 122:] == -7.0)
+
+
 @pytest.mark.parametrize("interp", ["gather", "bp"])
 def test_pscv_degenerate_inputs(interp):
     """What the reference's arithmetic does with degenerate inputs must come out the same: zero translation (s = 0: 0/0 in the

@@ -67,7 +67,11 @@ def pscv(b=8):
             L.check(L.lib.m4d_pscv_fused_fwd_ex(L.ptr(c1), L.ptr(c2), L.ptr(pt), L.ptr(pl), L.ptr(rot), 4, L.ptr(trans), L.ptr(cam["f"]),
                                                 L.ptr(cam["c"]), b, h, w, c, cuts, 4, L.ptr(cv), 9 * cuts, L.ptr(pd) if p9 else None, 9,
                                                 None if p9 else L.ptr(cl), 1, 0.5, None, mode, st))
-        variants = [(0, "gather"), (1, "bp"), (2, "bp_fma"), (0x200, "gather/tile"), (0x100, "gather/generic")]
+        if os.environ.get("PARA") == "insitu":      # what the random-weight bench model feeds level 2: parallax 0.6 .. 2.3
+            pl = 0.6 + 1.7 * torch.rand(b, h, w, 1, device="cuda", generator=g)
+        variants = [(0, "gather"), (0x400, "gather/warp"), (1, "bp"), (2, "bp_fma"), (0x200, "gather/tile"), (0x100, "gather/generic")]
+        if os.environ.get("VARIANTS"):
+            variants = [v for v in variants if v[1] in os.environ["VARIANTS"].split(",")]
         if os.environ.get("CPS"):
             variants = [((int(c[0]) << 16) | (int(c[1:] or 0) << 12), f"gather/var{c[0]}cps{c[1:]}") for c in os.environ["CPS"].split(",")] + [(0x200, "gather/tile")]
         for mode, name in variants:
