@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(256) pscv_kernel(PscvArgs a) {
             va = fma2(fma2(fma2(fma2(a00, w00, NZ2), ONE2, fma2(a01, w01, NZ2)), ONE2, fma2(a10, w10, NZ2)), ONE2, fma2(a11, w11, NZ2));
             vb = fma2(fma2(fma2(fma2(b00, w00, NZ2), ONE2, fma2(b01, w01, NZ2)), ONE2, fma2(b10, w10, NZ2)), ONE2, fma2(b11, w11, NZ2));
           } else {
-            va = fma2(a11, w11, fma2(a10, w10, fma2(a01, w01, fma2(a00, w00, NZ2))));
-            vb = fma2(b11, w11, fma2(b10, w10, fma2(b01, w01, fma2(b00, w00, NZ2))));
+            va = fma2(a11, w11, fma2(a10, w10, fma2(a00, w00, fma2(a01, w01, NZ2))));      // contraction of the reference binary
+            vb = fma2(b11, w11, fma2(b10, w10, fma2(b00, w00, fma2(b01, w01, NZ2))));
           }
         }
         float v0, v1, v2, v3;
@@ -404,8 +404,8 @@ __global__ void __launch_bounds__(FastCfg<C>::NT, 8) pscv9_kernel(FastArgs fa) {
           va = add2(add2(add2(fma2(a00, w00, NZ2), fma2(a01, w01, NZ2)), fma2(a10, w10, NZ2)), fma2(a11, w11, NZ2));
           vb = add2(add2(add2(fma2(b00, w00, NZ2), fma2(b01, w01, NZ2)), fma2(b10, w10, NZ2)), fma2(b11, w11, NZ2));
         } else {
-          va = fma2(a11, w11, fma2(a10, w10, fma2(a01, w01, fma2(a00, w00, NZ2))));
-          vb = fma2(b11, w11, fma2(b10, w10, fma2(b01, w01, fma2(b00, w00, NZ2))));
+          va = fma2(a11, w11, fma2(a10, w10, fma2(a00, w00, fma2(a01, w01, NZ2))));      // contraction of the reference binary
+          vb = fma2(b11, w11, fma2(b10, w10, fma2(b00, w00, fma2(b01, w01, NZ2))));
         }
       }
       float v0, v1, v2, v3;
@@ -675,8 +675,8 @@ __global__ void __launch_bounds__(128, WCfg<C, VAR>::MINB) pscv9w_kernel(WArgs w
             va = add2(add2(add2(fma2(a00, w00, NZ2), fma2(a01, w01, NZ2)), fma2(a10, w10, NZ2)), fma2(a11, w11, NZ2));
             vb = add2(add2(add2(fma2(b00, w00, NZ2), fma2(b01, w01, NZ2)), fma2(b10, w10, NZ2)), fma2(b11, w11, NZ2));
           } else {
-            va = fma2(a11, w11, fma2(a10, w10, fma2(a01, w01, fma2(a00, w00, NZ2))));
-            vb = fma2(b11, w11, fma2(b10, w10, fma2(b01, w01, fma2(b00, w00, NZ2))));
+            va = fma2(a11, w11, fma2(a10, w10, fma2(a00, w00, fma2(a01, w01, NZ2))));      // contraction of the reference binary
+            vb = fma2(b11, w11, fma2(b10, w10, fma2(b00, w00, fma2(b01, w01, NZ2))));
           }
         }
         float v0, v1, v2, v3;

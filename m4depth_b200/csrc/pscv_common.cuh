@@ -67,7 +67,7 @@ __device__ __forceinline__ float sample_scalar(const float* __restrict__ img, co
   } else if (MODE == kBP) {
     return FADD(FADD(FADD(FMUL(v00, t.w[0]), FMUL(v01, t.w[1])), FMUL(v10, t.w[2])), FMUL(v11, t.w[3]));
   } else {
-    return __fmaf_rn(v11, t.w[3], __fmaf_rn(v10, t.w[2], __fmaf_rn(v01, t.w[1], FMUL(v00, t.w[0]))));
+    return __fmaf_rn(v11, t.w[3], __fmaf_rn(v10, t.w[2], __fmaf_rn(v00, t.w[0], FMUL(v01, t.w[1]))));
   }
 }
 

@@ -34,7 +34,7 @@ from .cost_volumes import get_parallax_sweeping_cv, cost_volume, tile_in_batch
 from .network import (conv2d_same, leaky_relu, resize_bilinear_legacy, resize_nearest,
                       group_l2_normalize, DomainNormalization, FeaturePyramid, DispRefiner,
                       DepthEstimatorLevel, DepthEstimatorPyramid, M4Depth,
-                      M4depthAblationParameters, init_weights, level_channels)
+                      M4depthAblationParameters, init_weights, level_channels, reduction_order)
 from .metrics import depth_metrics, METRIC_NAMES
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -52,7 +52,7 @@ def _half_group_mean(prod_h, nbre_cuts, half_mode):
 
 
 def get_parallax_sweeping_cv(c1, c2, disp_prev_t, disp, rot, trans, camera, search_range,
-                             nbre_cuts=1, use_cuda_backproject=True, half_mode="fp32acc"):
+                             nbre_cuts=1, use_cuda_backproject=True, half_mode="fp32acc", back_project_fn=None):
     """-> (cv [b,h,w,cuts*(2r+1)] cut-major, prev_disp [b,h,w,2r+1])  (:223-281)."""
     b, h, w = c1.shape[0:3]
     n = 2 * search_range + 1
@@ -74,7 +74,7 @@ def get_parallax_sweeping_cv(c1, c2, disp_prev_t, disp, rot, trans, camera, sear
 
     c1_t = tile_in_batch(c1, n)                                    # :267
     comb = tile_in_batch(torch.cat((c2, disp_prev_t), dim=-1), n)  # :268
-    comb_w = dense_image_warp(comb, flow, use_cuda_backproject)    # :270
+    comb_w = dense_image_warp(comb, flow, use_cuda_backproject, back_project_fn)    # :270
     c2_w = comb_w[..., :-1]
     prev_disp = comb_w[..., -1]
 

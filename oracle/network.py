@@ -52,15 +52,60 @@ def same_padding(size, stride, k=3):
     return out, total // 2, total - total // 2
 
 
+# Summation order of the fp32 reductions whose order the reference does not define (Conv2D, the DomainNormalization means).
+# "default": torch's conv2d / mean.  "reordered": the same sums in another order (tap-major matmuls, row-then-column means) -
+# a second legitimate fp32 evaluation of the same graph; tests/test_oracle_golden.py and the GPU whole-model tests measure the
+# GPU-vs-oracle error against the oracle-vs-reordered-oracle error (what summation order alone does to the depth maps).
+# "fp64": every such reduction in double precision, rounded once (the least-error evaluation).
+REDUCTION_ORDER = "default"
+
+
+class reduction_order:
+    """Context manager: ``with oracle.network.reduction_order("reordered"): ...``"""
+
+    def __init__(self, mode):
+        assert mode in ("default", "reordered", "fp64"), mode
+        self.mode = mode
+
+    def __enter__(self):
+        global REDUCTION_ORDER
+        self.prev, REDUCTION_ORDER = REDUCTION_ORDER, self.mode
+
+    def __exit__(self, *a):
+        global REDUCTION_ORDER
+        REDUCTION_ORDER = self.prev
+
+
 def conv2d_same(x, kernel, bias, stride=1):
     """Keras Conv2D(k=3, padding='same') on NHWC input, HWIO kernel, bias add (no activation)."""
     b, h, w, cin = x.shape
-    _, pt, pb = same_padding(h, stride)
-    _, pl, pr = same_padding(w, stride)
+    oh, pt, pb = same_padding(h, stride)
+    ow, pl, pr = same_padding(w, stride)
+    if REDUCTION_ORDER == "reordered":
+        # tap-major: nine [pixels, cin] x [cin, cout] products accumulated in fp32 in raster order of the taps
+        xp = TF.pad(x, (0, 0, pl, pr, pt, pb))
+        y = torch.zeros(b, oh, ow, kernel.shape[3], dtype=F32)
+        for ky in range(3):
+            for kx in range(3):
+                sl = xp[:, ky:ky + (oh - 1) * stride + 1:stride, kx:kx + (ow - 1) * stride + 1:stride, :]
+                y = y + (sl.reshape(-1, cin) @ kernel[ky, kx]).reshape(b, oh, ow, -1)
+        return y + bias.view(1, 1, 1, -1)
     xn = TF.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
     wt = kernel.permute(3, 2, 0, 1).contiguous()
-    y = TF.conv2d(xn, wt, bias, stride=stride)
+    if REDUCTION_ORDER == "fp64":
+        y = TF.conv2d(xn.double(), wt.double(), bias.double(), stride=stride).to(F32)
+    else:
+        y = TF.conv2d(xn, wt, bias, stride=stride)
     return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _mean_hw(t):
+    """mean over H and W (keepdim) in the summation order REDUCTION_ORDER selects."""
+    if REDUCTION_ORDER == "reordered":
+        return t.mean(dim=2, keepdim=True).mean(dim=1, keepdim=True)
+    if REDUCTION_ORDER == "fp64":
+        return t.double().mean(dim=(1, 2), keepdim=True).to(F32)
+    return t.mean(dim=(1, 2), keepdim=True)
 
 
 def resize_bilinear_legacy(x, out_h, out_w):
@@ -120,9 +165,9 @@ class DomainNormalization:
         self.bias = bias.reshape(1, 1, 1, -1).to(F32)
 
     def __call__(self, f_map):
-        mean = f_map.mean(dim=(1, 2), keepdim=True)
+        mean = _mean_hw(f_map)
         dev = f_map - mean
-        var = (dev * dev).mean(dim=(1, 2), keepdim=True)       # tf.math.reduce_variance
+        var = _mean_hw(dev * dev)                              # tf.math.reduce_variance
         g = dev / (var + 1e-12)
         sq = (g * g).sum(dim=-1, keepdim=True)
         normed = g * torch.rsqrt(torch.clamp(sq, min=1e-12))   # tf.math.l2_normalize

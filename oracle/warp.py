@@ -134,11 +134,13 @@ def back_project_grad(inputs, coords, grad):
     return igrad.reshape(B, H, W, Fd, C), torch.stack((gx, gy), dim=-1)
 
 
-def dense_image_warp(image, flow, use_cuda_backproject=False):
+def dense_image_warp(image, flow, use_cuda_backproject=False, back_project_fn=None):
     """image [b,h,w,c], flow [b,h,w,2] (row, col) -> [b,h,w,c]; query = grid + flow (:244).
 
     ``use_cuda_backproject`` selects the branch at :246-253 (clip to the image, reverse to (x,y),
-    BackProject with S=F=1) instead of the python gather path at :255-259.
+    BackProject with S=F=1) instead of the python gather path at :255-259.  ``back_project_fn`` replaces the
+    restated BackProject by another implementation of the op - the tests pass the reference's own compiled kernel
+    (``oracle.ref_binary.back_project``) here.
     """
     b, h, w, c = image.shape
     gy = torch.arange(h, dtype=F32).view(1, h, 1).expand(1, h, w)
@@ -150,6 +152,6 @@ def dense_image_warp(image, flow, use_cuda_backproject=False):
         hi = torch.tensor([float(h - 1), float(w - 1)], dtype=F32)
         q = torch.minimum(torch.maximum(q, lo), hi)
         coords = torch.flip(q, dims=[-1]).reshape(b, h, w, 1, 1, 2)
-        out = back_project(image.unsqueeze(-2), coords)
+        out = (back_project_fn or back_project)(image.unsqueeze(-2), coords)
         return out.reshape(b, h, w, c)
     return interpolate_bilinear(image, q.reshape(b, h * w, 2)).reshape(b, h, w, c)

@@ -225,6 +225,8 @@ LEVEL_SHAPES = [  # (name, b, h, w, c, cuts, camera kind): the level shapes of B
     ("cfg3_l3", 2, 48, 160, 64, 2, "kitti"), ("cfg3_l5", 2, 12, 40, 128, 4, "kitti"),
     ("cfg3_l6", 8, 6, 20, 192, 8, "kitti"), ("cfg5_l6", 2, 8, 10, 192, 8, "tartan"),
     ("cfg5_l5", 1, 15, 20, 128, 4, "tartan"), ("ragged", 3, 5, 7, 32, 2, "kitti"),
+    ("cfg3_l1", 1, 192, 640, 16, 1, "kitti"), ("cfg3_l2", 1, 96, 320, 32, 2, "kitti"), ("cfg5_l1", 1, 240, 320, 16, 1, "tartan"),
+    ("cfg5_l2", 1, 120, 160, 32, 2, "tartan"), ("cfg5_l3", 1, 60, 80, 64, 2, "tartan"), ("cfg5_l4", 1, 30, 40, 96, 4, "tartan"),
 ]
 
 
@@ -545,6 +547,81 @@ def test_backproject_op_vs_oracle():
     inp8 = torch.randn(B, H, W, Fd, 8, generator=g)
     np.testing.assert_allclose(m.utils.back_project(cu(inp8), cu(coords)).cpu().numpy(),
                                oracle.back_project(inp8, coords).numpy(), rtol=0, atol=1e-6)
+
+
+# ------------------------------------------------------- the reference's own compiled BackProject kernels as the oracle
+def _ref_binary():
+    from oracle import ref_binary
+    if not ref_binary.available():
+        pytest.fail("oracle/_ref/libbackproject_ref.so is missing: __graft_entry__.build() compiles it from /root/reference "
+                    "(cuda_backproject/backproject_op_gpu.cu.cc, unmodified) and it travels with the snapshot")
+    return ref_binary
+
+
+def _bp_case(shape, seed):
+    B, H, W, S, Fd, C = shape
+    g = torch.Generator().manual_seed(seed)
+    inp = torch.randn(B, H, W, Fd, C, generator=g)
+    coords = torch.rand(B, H, W, S, Fd, 2, generator=g) * torch.tensor([W + 2.0, H + 2.0]) - 1.0
+    coords[0, 0, 0, 0, 0, 0] = float("nan")
+    coords[0, 1, 1, 0, 0] = torch.tensor([3.0, 2.0])            # integral coordinate: ceil == floor
+    coords[-1, 2, 2, -1, -1] = torch.tensor([W - 1.0, H - 1.0])   # last pixel
+    coords[0, 2, 1, 0, 0] = torch.tensor([0.0, 0.0])
+    return inp, coords, g
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 9, 3, 2, 5), (1, 12, 16, 9, 1, 32), (2, 6, 5, 1, 1, 33), (1, 4, 4, 2, 3, 8),
+                                   (9, 24, 80, 1, 1, 33), (2, 48, 64, 1, 1, 16)])
+def test_backproject_fwd_equals_reference_binary(shape):
+    """m4d_backproject_fwd against BackProjectForwardLauncher of the reference itself (backproject_op_gpu.cu.cc:19-103 compiled
+    unmodified for sm_100a): every output bit, including the zeros the reference gets from its memset where the coordinate is
+    outside the image or NaN.  (9, 24, 80, 1, 1, 33) is the shape class the reference runs it on: 9b tiled copies, c+1 channels.)"""
+    m = _m4d()
+    ref = _ref_binary()
+    inp, coords, _ = _bp_case(shape, 17 + shape[5])
+    want = ref.back_project(inp, coords)
+    got = m.utils.back_project(cu(inp), cu(coords)).cpu()
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    # and the restated oracle the CPU tests use is within one rounding of the binary (it rounds the products separately)
+    np.testing.assert_allclose(oracle.back_project(inp, coords).numpy(), want.numpy(), rtol=0, atol=4e-7 * float(inp.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 9, 3, 2, 5), (1, 12, 16, 9, 1, 32), (2, 6, 5, 1, 1, 33), (1, 4, 4, 2, 3, 8)])
+def test_backproject_bwd_vs_reference_binary(shape):
+    """m4d_backproject_bwd against BackProjectBackwardLauncher of the reference (:108-223).  Both scatter-add inputs_grad with
+    floating-point atomics (order not fixed: 1e-5 of the scale); the reference sums coords_grad serially over the channels,
+    libm4d in a fixed shuffle order (1e-5 of the scale)."""
+    m = _m4d()
+    ref = _ref_binary()
+    inp, coords, g = _bp_case(shape, 23 + shape[5])
+    grad = torch.randn(*coords.shape[:-1], shape[5], generator=g)
+    want_i, want_c = ref.back_project_grad(inp, coords, grad)
+    got_i, got_c = m.utils.back_project_grad(cu(inp), cu(coords), cu(grad))
+    np.testing.assert_allclose(got_i.cpu().numpy(), want_i.numpy(), rtol=1e-5, atol=1e-5 * float(want_i.abs().max()))
+    np.testing.assert_allclose(got_c.cpu().numpy(), want_c.numpy(), rtol=1e-4, atol=1e-5 * float(want_c.abs().max()))
+    # the restated oracle gradient agrees with the binary as well
+    oi, oc = oracle.back_project_grad(inp, coords, grad)
+    np.testing.assert_allclose(oi.numpy(), want_i.numpy(), rtol=1e-5, atol=1e-5 * float(want_i.abs().max()))
+    np.testing.assert_allclose(oc.numpy(), want_c.numpy(), rtol=1e-4, atol=1e-5 * float(want_c.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 80, 32, 2), (1, 37, 53, 16, 1), (1, 12, 40, 128, 4), (2, 6, 20, 192, 8)])
+def test_pscv_bp_fma_equals_pipeline_through_reference_binary(shape):
+    """The fused PSCV in BP_FMA mode against the reference pipeline with the reference's OWN compiled BackProject kernel doing
+    the warp: utils/depth_operations.py:223-281 restated literally (9x tile_in_batch copies, clip, reverse, BackProject with
+    S = F = 1 on the [9b, h, w, c+1] tensor, fp16 correlate) where the BackProject call is the binary.  cv and prev_disp bit for
+    bit: this is the arithmetic of the reference's GPU path."""
+    m = _m4d()
+    ref = _ref_binary()
+    b, h, w, c, cuts = shape
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(800 + h + c, b, h, w, c, cuts, "kitti")
+    pl[:, : h // 3] -= 5.0
+    want_cv, want_pd = oracle.get_parallax_sweeping_cv(c1, c2, pt, pl, rot, trans, cam, 4, nbre_cuts=cuts, use_cuda_backproject=True,
+                                                       back_project_fn=ref.back_project)
+    cv, pd = m.utils.get_parallax_sweeping_cv(cu(c1), cu(c2), cu(pt), cu(pl), cu(rot), cu(trans), dev_cam(cam), 4, nbre_cuts=cuts,
+                                              interp=m.INTERP_BP_FMA)
+    assert torch.equal(pd.cpu().view(torch.int32), want_pd.view(torch.int32))
+    assert torch.equal(cv.cpu().view(torch.int32), want_cv.view(torch.int32))
 
 
 @pytest.mark.parametrize("shape", [(2, 7, 9, 3, 2, 5), (1, 12, 16, 9, 1, 32), (2, 6, 5, 1, 1, 33), (1, 4, 4, 2, 3, 8)])
@@ -1110,3 +1187,140 @@ def test_model_streaming_graph_equals_eager():
     for a, bb in zip(outs[False], outs[True]):
         assert torch.equal(a, bb)
     assert float(outs[True][0].min()) == 1000.0        # frame 0 is the new-trajectory pass-through
+
+
+# ----------------------------------------------------- whole model at the BASELINE.json sizes, bounded by oracle-vs-oracle
+def _synth():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if os.path.join(root, "tools") not in sys.path:
+        sys.path.insert(0, os.path.join(root, "tools"))
+    import synth
+    return synth
+
+
+def _report(name, rows):
+    """Per-frame error table of a whole-model comparison -> gpurun_out/ (numbers quoted in DESIGN.md)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"model_parity_{name}.json"), "w") as f:
+        json.dump(rows, f, indent=1)
+
+
+def _gpu_sequence(m, frames, cam, nl, new_traj_at=(0,), graph=True, weights_seed=1):
+    model = m.M4Depth(nbre_levels=nl, use_cuda_graph=graph)
+    model.load_weights(oracle.init_weights(nl, seed=weights_seed, bias_std=0.05, dn_random=True))
+    dcam = dev_cam(cam)
+    outs = []
+    for t, fr in enumerate(frames):
+        b = fr["RGB_im"].shape[0]
+        s = {"RGB_im": cu(fr["RGB_im"]), "rot": cu(fr["rot"]), "trans": cu(fr["trans"]), "new_traj": [t in new_traj_at] * b}
+        outs.append(model([[s], dcam])["depth"].cpu().clone())
+    return outs
+
+
+def _oracle_sequence(frames, cam, nl, mode, new_traj_at=(0,), weights_seed=1):
+    w = oracle.init_weights(nl, seed=weights_seed, bias_std=0.05, dn_random=True)
+    outs = []
+    with oracle.reduction_order(mode), torch.no_grad():
+        model = oracle.M4Depth(w, nbre_levels=nl, pscv_kwargs={"use_cuda_backproject": False})
+        for t, fr in enumerate(frames):
+            s = dict(fr)
+            s["new_traj"] = torch.tensor([t in new_traj_at] * fr["RGB_im"].shape[0])
+            outs.append(model([[s], cam])["depth"].clone())
+    return outs
+
+
+QS = (0.5, 0.9, 0.99, 0.999)
+
+
+def _err(x, y):
+    e = ((x - y).abs() / (y.abs() + 0.1)).flatten().double()
+    return [float(torch.quantile(e, q)) for q in QS], float(e.max()), float((e <= 1e-4).double().mean())
+
+
+def _check_against_oracle_pair(name, gpu, ref, alt, f64, new_traj_at=(0,)):
+    """GPU-vs-oracle error against the error between CPU evaluations of the same graph that differ only in how the fp32
+    reductions are summed (tests/test_oracle_golden.py::test_summation_order_alone_moves_the_depth_maps).
+      * pass-through frame of a trajectory start: exact;
+      * first estimated frame: 1e-4 (north_star) at the 99.9th percentile and for at least 99.9 % of the pixels;
+      * every estimated frame: every quantile (50 / 90 / 99 / 99.9 %) of the GPU error within 4x the larger of the two
+        oracle-vs-oracle errors at that quantile, the maximum (one pixel: a noisy statistic) within 10x, the fraction of pixels
+        inside 1e-4 within 3 points of the oracles'.
+    Why 4x and not 1x: besides summation order the GPU path differs from the torch oracle in expf / logf / rsqrt (<= 2 ulp
+    each) and in the 3xFP16 split products of the tensor-core convolutions (2^-22 relative per product); measured on B200 the
+    ratio is 2-3x at every quantile and does not grow with the frame index (gpurun_out/model_parity_*.json)."""
+    rows = []
+    since = 0
+    for t in range(len(gpu)):
+        since = 0 if t in new_traj_at else since + 1
+        qg, mg, ing = _err(gpu[t], ref[t])
+        qa, ma, ina = _err(alt[t], ref[t])
+        qb, mb, inb = _err(f64[t], ref[t])
+        rows.append({"frame": t, "frames_since_reset": since, "gpu_vs_oracle": {"q": qg, "max": mg, "within_1e-4": ing},
+                     "reordered_vs_oracle": {"q": qa, "max": ma, "within_1e-4": ina}, "fp64_vs_oracle": {"q": qb, "max": mb, "within_1e-4": inb}})
+    _report(name, rows)
+    K_ = 4.0
+    for r in rows:
+        t, g_ = r["frame"], r["gpu_vs_oracle"]
+        omax = max(r["reordered_vs_oracle"]["max"], r["fp64_vs_oracle"]["max"])
+        if r["frames_since_reset"] == 0:
+            assert g_["max"] == 0.0, (name, t, g_)
+        else:
+            if r["frames_since_reset"] == 1:
+                assert g_["within_1e-4"] >= 0.999 and g_["q"][3] <= 1e-4, (name, t, g_)
+            for i, q in enumerate(QS):
+                bound = K_ * max(r["reordered_vs_oracle"]["q"][i], r["fp64_vs_oracle"]["q"][i]) + 2e-6
+                assert g_["q"][i] <= bound, (name, t, q, g_["q"][i], bound)
+            assert g_["max"] <= 10.0 * omax + 1e-4, (name, t, g_["max"], omax)
+            assert g_["within_1e-4"] >= min(r["reordered_vs_oracle"]["within_1e-4"], r["fp64_vs_oracle"]["within_1e-4"]) - 0.03, (name, t)
+
+
+BASELINE_MODEL_CASES = [  # (name, camera, b, H, W, frames): BASELINE.json configs[1], [2] (two of the eight sequences), [4]
+    ("cfg1_384x384", "midair", 1, 384, 384, 5),
+    ("cfg2_384x1280", "kitti", 2, 384, 1280, 5),
+    ("cfg4_480x640", "tartan", 1, 480, 640, 5),
+]
+
+
+@pytest.mark.parametrize("case", BASELINE_MODEL_CASES, ids=[c[0] for c in BASELINE_MODEL_CASES])
+def test_model_vs_oracle_at_baseline_configs(case):
+    """Whole model (6 levels, CUDA graphs) against the oracle model at the BASELINE.json image sizes, four estimated frames."""
+    m = _m4d()
+    name, kind, b, H, W, n = case
+    frames, cam = _synth().synth_sequence(n, b, H, W, kind, seed=1234 + H + W)
+    gpu = _gpu_sequence(m, frames, cam, 6)
+    ref = _oracle_sequence(frames, cam, 6, "default")
+    alt = _oracle_sequence(frames, cam, 6, "reordered")
+    f64 = _oracle_sequence(frames, cam, 6, "fp64")
+    _check_against_oracle_pair(name, gpu, ref, alt, f64)
+
+
+def test_model_batch_independence_at_headline_config():
+    """BASELINE configs[2] as benched (384x1280, b = 8): each of the eight sequences gets bit for bit the depth maps it gets in
+    a batch of two (the pair the oracle comparison above runs), frame by frame - no kernel mixes batch elements."""
+    m = _m4d()
+    frames, cam = _synth().synth_sequence(4, 2, 384, 1280, "kitti", seed=1234 + 384 + 1280)
+    two = _gpu_sequence(m, frames, cam, 6)
+    rep = lambda t: t.repeat(4, *([1] * (t.dim() - 1)))
+    frames8 = [{k: rep(v) for k, v in fr.items()} for fr in frames]
+    cam8 = {k: rep(v) for k, v in cam.items()}
+    eight = _gpu_sequence(m, frames8, cam8, 6)
+    for a_, b_ in zip(two, eight):
+        assert torch.equal(rep(a_).view(torch.int32), b_.view(torch.int32))
+
+
+def test_model_16_frame_stream_drift():
+    """BASELINE configs[4]-shaped stream (TartanAir camera, 16 frames, a trajectory restart at frame 9; 240x320 so that the three
+    CPU evaluations stay within a minute): the recurrent state (m4depth_network.py:160-163) carried over many frames stays
+    within the oracle-vs-oracle envelope at every frame, and the restart brings the error back to the first-frame bound."""
+    m = _m4d()
+    frames, cam = _synth().synth_sequence(16, 1, 240, 320, "tartan", seed=4242)
+    at = (0, 9)
+    gpu = _gpu_sequence(m, frames, cam, 6, new_traj_at=at)
+    ref = _oracle_sequence(frames, cam, 6, "default", new_traj_at=at)
+    alt = _oracle_sequence(frames, cam, 6, "reordered", new_traj_at=at)
+    f64 = _oracle_sequence(frames, cam, 6, "fp64", new_traj_at=at)
+    _check_against_oracle_pair("stream16_240x320", gpu, ref, alt, f64, new_traj_at=at)

@@ -76,8 +76,8 @@ def check_depth(got, want, frame):
     Frames 0/1: every pixel within 1e-4.  Later frames: an fp32 summation-order difference of 1e-7
     moves a query point enough to flip an fp16 rounding inside the PSCV (1 fp16 ulp = 5e-4 relative)
     and the flip propagates through the refiner, so the bound is statistical: median 1e-5,
-    99th percentile 1e-3, max 1e-2.  (Two CPU evaluations of the reference's own graph that differ
-    only in reduce_mean order show exactly this; see DESIGN.md.)
+    99th percentile 1e-3, max 1e-2.  Two CPU evaluations of the reference's own graph that differ
+    only in summation order show exactly this: test_summation_order_alone_moves_the_depth_maps below.
     """
     err = np.abs(got - want) / (np.abs(want) + 0.1)
     if frame <= 1:
@@ -179,3 +179,51 @@ def test_plain_c_restatement_of_the_backproject_kernels_agrees_with_the_torch_or
     want_i, want_c = oracle.back_project_grad(inp, coords, grad)
     np.testing.assert_allclose(ig.numpy(), want_i.numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(cg.numpy(), want_c.numpy(), rtol=1e-5, atol=1e-5)
+
+
+def depth_err_quantiles(x, y, qs=(0.5, 0.9, 0.99, 0.999)):
+    """Relative depth error |x - y| / (|y| + 0.1): the quantiles in ``qs``, the maximum and the fraction within 1e-4."""
+    err = ((x - y).abs() / (y.abs() + 0.1)).flatten().double()
+    return [float(torch.quantile(err, q)) for q in qs], float(err.max()), float((err <= 1e-4).double().mean())
+
+
+def run_oracle_sequence(frames, cam, nl, mode, weights_seed=1):
+    """The oracle model over a sequence under one summation order (oracle.network.REDUCTION_ORDER); depth map per frame."""
+    w = oracle.init_weights(nl, seed=weights_seed, bias_std=0.05, dn_random=True)
+    outs = []
+    with oracle.reduction_order(mode), torch.no_grad():
+        model = oracle.M4Depth(w, nbre_levels=nl, pscv_kwargs={"use_cuda_backproject": False})
+        for t, fr in enumerate(frames):
+            s = dict(fr)
+            s["new_traj"] = torch.tensor([t == 0] * fr["RGB_im"].shape[0])
+            outs.append(model([[s], cam])["depth"].clone())
+    return outs
+
+
+def test_summation_order_alone_moves_the_depth_maps():
+    """What the north-star tolerance (1e-4 relative) can and cannot mean for the recurrent model.  The SAME reference graph
+    evaluated twice on the CPU in fp32 - convolutions and DomainNormalization means summed in two different orders, and once
+    more with those reductions in fp64 - agrees to 1e-4 on the first estimated frame, and then diverges: an fp32 rounding
+    difference flips an fp16 rounding in the PSCV (1 fp16 ulp = 5e-4), the refiner and exp() amplify it, and the recurrent
+    state carries it on.  By the third estimated frame the 99th percentile of the error BETWEEN TWO CPU EVALUATIONS is beyond
+    1e-3.  The GPU whole-model tests therefore bound the GPU-vs-oracle error by this oracle-vs-oracle error
+    (tests/test_gpu_parity.py::test_model_vs_oracle_at_baseline_configs), not by a fixed number."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from synth import synth_sequence
+    frames, cam = synth_sequence(5, 1, 128, 192, "kitti", seed=77)
+    ref = run_oracle_sequence(frames, cam, 6, "default")
+    alt = run_oracle_sequence(frames, cam, 6, "reordered")
+    f64 = run_oracle_sequence(frames, cam, 6, "fp64")
+    assert torch.equal(ref[0], alt[0]) and float(ref[0].min()) == 1000.0          # frame 0: new-trajectory pass-through
+    q1, mx1, in1 = depth_err_quantiles(alt[1], ref[1])
+    assert mx1 <= 1e-4 and in1 == 1.0, (q1, mx1)                                  # first estimated frame: 1e-4 everywhere
+    grew = []
+    for t in range(2, 5):
+        qa, mxa, ina = depth_err_quantiles(alt[t], ref[t])
+        qb, mxb, inb = depth_err_quantiles(f64[t], ref[t])
+        grew.append((qa[2], qb[2], ina))
+        assert qa[0] <= 1e-4 and qb[0] <= 1e-4                                     # the bulk stays close ...
+    assert grew[-1][0] > 1e-4 and grew[-1][1] > 1e-4 and grew[-1][2] < 1.0         # ... the tail does not, whatever the order
+    assert grew[-1][0] > grew[0][0]                                                # and it grows with the recurrence
