@@ -36,12 +36,17 @@ extern std::atomic<uint64_t> g_m4d_launches;
     }                                                                            \
   } while (0)
 
+// SM count of the CURRENT device, cached per device id (a process may drive several GPUs; relaxed atomics: every thread
+// that races on the first call stores the same value).
 static inline int m4d_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;  // B200
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  const int slot = dev & 63;
+  int n = cache[slot].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;  // B200
+    cache[slot].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -929,11 +929,12 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
                                       conv3x3_tc_kernel<false, false, true>,  conv3x3_tc_kernel<false, true, true>,
                                       conv3x3_tc_kernel<true, false, true>,   conv3x3_tc_kernel<true, true, true>};
   // function attributes are per device: remember which devices of this process have them
-  static bool attr_set_dev[64] = {};
+  // (atomic flags: two host threads racing on the first call both set the attributes, which is idempotent)
+  static std::atomic<bool> attr_set_dev[64];
   int dev_id = 0;
   cudaGetDevice(&dev_id);
-  bool& attr_set = attr_set_dev[dev_id & 63];
-  if (!attr_set) {
+  std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
+  if (!attr_set.load(std::memory_order_acquire)) {
     for (int i = 0; i < 8; ++i) {
       cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
@@ -941,7 +942,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
         return M4D_ECUDA;
       }
     }
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const int grid = a.nitems < m4d_sm_count() ? a.nitems : m4d_sm_count();
   kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)]<<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);

@@ -37,6 +37,24 @@ M4depthAblationParameters = namedtuple(
 
 LEAKY = 0.1
 
+# How often a convolution that could have used the tensor cores did not (odd-sized stride-2 input, unaligned or strided view):
+# {reason: count}.  The FFMA2 kernel gives the same results at a fraction of the rate; m4depth_b200.m4depth_network.conv_fallbacks
+# lets a caller see it (the first occurrence of each reason is also logged once).
+conv_fallbacks = {}
+
+
+def _note_fallback(reason, shape):
+    n = conv_fallbacks.get(reason, 0)
+    conv_fallbacks[reason] = n + 1
+    if n == 0:
+        import warnings
+        warnings.warn(f"m4depth_b200: convolution off the tcgen05 path ({reason}; input {tuple(shape)}): FFMA2 kernel used", stacklevel=3)
+
+
+def _nvtx(name):
+    """NVTX range around a host-side section (eager passes and CUDA-graph capture; graph replays launch nothing from Python)."""
+    return torch.cuda.nvtx.range(name)
+
 
 def _pix_stride(t):
     """Pixel stride (floats) of a [b,h,w,c] tensor laid out as rows of pixels, possibly inside a wider buffer."""
@@ -111,9 +129,13 @@ class _Conv2D:
         xs, ys = _pix_stride(x), _pix_stride(out)
         algo = algo or DEFAULT_CONV_ALGO
         # algo: 0 = auto (tcgen05 3xTF32 where the layer was packed and the strides allow, else FFMA2), 1 = FFMA2, 2 = tcgen05
-        tc_ok = self.packed is not None and xs % 4 == 0 and cin >= self.tc_min_cin
-        if self.strides == 2:       # the 2x2-cell formulation: even sizes (TF SAME pads bottom / right only), dense pixels
-            tc_ok = tc_ok and h % 2 == 0 and w % 2 == 0 and xs == cin
+        tc_ok = self.packed is not None and cin >= self.tc_min_cin
+        if tc_ok and not (xs % 4 == 0 and x.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0):
+            tc_ok = False           # TMA needs 16-byte aligned bases and pixel strides
+            _note_fallback("unaligned view", x.shape)
+        if tc_ok and self.strides == 2 and not (h % 2 == 0 and w % 2 == 0 and xs == cin):
+            tc_ok = False           # the 2x2-cell formulation: even sizes (TF SAME pads bottom / right only), dense pixels
+            _note_fallback("stride 2 on an odd-sized or strided input", x.shape)
         if algo != 1 and tc_ok:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -347,22 +369,26 @@ class DepthEstimatorLevel:
         if self.pscv_events is not None:               # bench.py: CUDA events around this launch (in-situ roofline)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
+        torch.cuda.nvtx.range_push("get_parallax_sweeping_cv")          # reference scope: m4depth_network.py:216-221
         L.check(L.lib.m4d_pscv_fused_fwd_ex(
             L.ptr(cur), L.ptr(prev_f_maps), L.ptr(self._para_prev_t) if want_prev else None, L.ptr(self._para_prev_l),
             L.ptr(rot), rd, L.ptr(trans), L.ptr(cam_f), L.ptr(cam_c), b, h, w, c, cuts, 4,
             self._x_in.data_ptr() + 4 * self.ch_cv, self.xs, None, 0,
             (self._x_in.data_ptr() + 4 * self.ch_logprev) if want_prev else None, self.xs, scale, None,
             self.interp, st))
+        torch.cuda.nvtx.range_pop()
         if self.pscv_events is not None:
             ev1.record()
             self.pscv_events.append((ev0, ev1))
         # :232 SNCV
         if self.ch_sncv >= 0:
-            L.check(L.lib.m4d_sncv_fwd(L.ptr(cur), L.ptr(cur), b, h, w, c, cuts, 3,
-                                       self._x_in.data_ptr() + 4 * self.ch_sncv, self.xs, st))
+            with _nvtx("cost_volume"):                              # m4depth_network.py:232
+                L.check(L.lib.m4d_sncv_fwd(L.ptr(cur), L.ptr(cur), b, h, w, c, cuts, 3,
+                                           self._x_in.data_ptr() + 4 * self.ch_sncv, self.xs, st))
         f_input = self._x_in[..., :self.cin]
         # :245 refiner
-        prev_out = self.disp_refiner(f_input)
+        with _nvtx("DispRefiner"):                                  # m4depth_network.py:244-245
+            prev_out = self.disp_refiner(f_input)
         r = prev_out[0]
         # :247-260 epilogue + state update
         L.check(L.lib.m4d_level_epilogue(L.ptr(r), _pix_stride(r), L.ptr(rot), rd, L.ptr(trans), L.ptr(cam_f), L.ptr(cam_c),
@@ -405,7 +431,8 @@ class DepthEstimatorPyramid:
                 level = self.levels[l]
                 local_camera = {"f": self._cam[0][l], "c": self._cam[1][l]}
                 d_est = dict(d_est_curr[-1]) if d_est_curr else None
-                est = level(f_pyr_curr[l], d_est, rot, trans, local_camera, new_traj)
+                with _nvtx(f"DepthEstimatorLevel/{l + 1}"):
+                    est = level(f_pyr_curr[l], d_est, rot, trans, local_camera, new_traj)
                 d_est_curr = [est] if d_est_curr is None else d_est_curr + [est]
             d_est_seq.append(d_est_curr[::-1])
         return d_est_seq
@@ -439,6 +466,7 @@ class M4Depth:
         self._static = None
         self._out = None
         self._h2d = None            # side-stream upload state for host (CPU) frames
+        self._inputs_event = None   # see inputs_consumed()
 
     # ------------------------------------------------------------------------------------------ weights
     def weight_layers(self):
@@ -457,15 +485,50 @@ class M4Depth:
 
     def load_weights(self, weights):
         """weights: {"encoder/conv_layers_s1/0/kernel": tensor[3,3,cin,cout], ".../bias": tensor[cout], ...,
-        "encoder/dn_layers/0/scale"|"bias": tensor[1,1,1,16]} (torch tensors or numpy arrays)."""
+        "encoder/dn_layers/0/scale"|"bias": tensor[1,1,1,16]} (torch tensors or numpy arrays).  A checkpoint trained without
+        DINL has no dn variables (Keras builds DomainNormalization on its first call only): they are required only when this
+        model uses DINL.  Kernel shapes are checked against the layout this model's ablation settings imply."""
         as_t = lambda v: v if isinstance(v, torch.Tensor) else torch.as_tensor(v)
-        for prefix, layer in self.weight_layers().items():
-            layer.assign(as_t(weights[prefix + "/kernel"]), as_t(weights[prefix + "/bias"]), self.device)
+        layers = self.weight_layers()
+        need = [k + sfx for k in layers for sfx in ("/kernel", "/bias")]
+        if self.encoder.use_dinl:
+            need += ["encoder/dn_layers/0/scale", "encoder/dn_layers/0/bias"]
+        missing = [k for k in need if k not in weights]
+        if missing:
+            raise L.M4DError(f"load_weights: {len(missing)} variables missing from the checkpoint, e.g. {missing[:4]}")
+        expect = self._expected_cin()
+        for prefix, layer in layers.items():
+            k = as_t(weights[prefix + "/kernel"])
+            if k.dim() == 4 and prefix in expect and k.shape[2] != expect[prefix]:
+                raise L.M4DError(f"load_weights: {prefix}/kernel has {k.shape[2]} input channels, this model's layout "
+                                 f"(ablation {tuple(self.ablation_settings)}) needs {expect[prefix]}")
+            layer.assign(k, as_t(weights[prefix + "/bias"]), self.device)
         dn = self.encoder.dn_layers[0]
-        dn.scale = as_t(weights["encoder/dn_layers/0/scale"]).to(self.device, torch.float32).reshape(1, 1, 1, -1).contiguous()
-        dn.bias = as_t(weights["encoder/dn_layers/0/bias"]).to(self.device, torch.float32).reshape(1, 1, 1, -1).contiguous()
+        if self.encoder.use_dinl:
+            dn.scale = as_t(weights["encoder/dn_layers/0/scale"]).to(self.device, torch.float32).reshape(1, 1, 1, -1).contiguous()
+            dn.bias = as_t(weights["encoder/dn_layers/0/bias"]).to(self.device, torch.float32).reshape(1, 1, 1, -1).contiguous()
         self._graphs.clear()
         self._seen.clear()
+
+    def _expected_cin(self):
+        """{layer prefix: input channels} of this model's layout (m4depth_network.py:59,102,109,223-242)."""
+        ab, d = self.ablation_settings, {}
+        cin = 3
+        for i, n in enumerate(self.encoder.out_sizes):
+            d[f"encoder/conv_layers_s1/{i}"] = cin
+            d[f"encoder/conv_layers_s2/{i}"] = n
+            cin = n
+        for i, _ in enumerate(self.d_estimator.levels):
+            cuts = 2 ** ((i + 1) // 2) if ab.subdivide_features else 1
+            cin = 9 * cuts + 1 + (4 if ab.level_memory else 0) + (49 * cuts if ab.SNCV else 0) + (1 if ab.time_recurr else 0)
+            pfx = f"d_estimator/levels/{i}/disp_refiner"
+            for j, n in enumerate((128, 128, 96)):
+                d[f"{pfx}/prep_conv_layers/{j}"] = cin
+                cin = n
+            for j, n in enumerate((64, 32, 16, 5)):
+                d[f"{pfx}/est_d_conv_layers/{j}"] = cin
+                cin = n
+        return d
 
     def load_checkpoint(self, source, which=None):
         """Load a reference checkpoint: a TF tensor-bundle prefix (``.../cp-0071.ckpt``, what callbacks.py:119-129 saves)
@@ -488,7 +551,10 @@ class M4Depth:
         # The recurrent state lives in the levels, so this is the same computation.  Only the last frame's maps stay valid.
         d_maps_pyrs = []
         for s in traj_samples:
-            d_maps_pyrs += self.d_estimator([self.encoder(s['RGB_im'])], [s], camera, False)
+            with _nvtx("M4Depth/encoder"):
+                pyr = self.encoder(s['RGB_im'])
+            with _nvtx("M4Depth/d_estimator"):
+                d_maps_pyrs += self.d_estimator([pyr], [s], camera, False)
         h, w = traj_samples[-1]['RGB_im'].shape[1:3]
         d1 = d_maps_pyrs[-1][0]["depth"]
         b, ih, iw, _ = d1.shape
@@ -500,13 +566,30 @@ class M4Depth:
     def _parity(self):
         return self.d_estimator.levels[0]._parity if self.d_estimator.levels[0].shape else 0
 
+    def inputs_consumed(self):
+        """CUDA event recorded after the last asynchronous read of the caller's input tensors by the most recent ``call``.
+        With pinned HOST inputs ``call`` returns before the uploads have run: wait for this event (``.synchronize()`` or
+        ``stream.wait_event``) before refilling the same host buffers ("Lifetime of input buffers")."""
+        return self._inputs_event
+
     def call(self, data, training=False):
         if training:
             raise NotImplementedError("m4depth_b200 implements the inference path only (training=False)")
+        with torch.cuda.device(self.device):            # buffers live on self.device: launch on that device's current stream
+            out = self._call(data)
+            if self._inputs_event is None:
+                self._inputs_event = torch.cuda.Event()
+                self._inputs_event.record()
+            return out
+
+    def _call(self, data):
         traj_samples, camera = data[0], data[1]
         self.step_counter += 1
         if not (self.use_cuda_graph and len(traj_samples) == 1):
             self._forward(traj_samples, camera)
+            if self._inputs_event is None:
+                self._inputs_event = torch.cuda.Event()
+            self._inputs_event.record()
             return {"depth": self._out}
 
         s = traj_samples[0]
@@ -548,6 +631,11 @@ class M4Depth:
         st["trans"].copy_(s['trans'], non_blocking=True)
         st["f"].copy_(camera["f"], non_blocking=True)
         st["c"].copy_(camera["c"], non_blocking=True)
+        if self._inputs_event is None:
+            self._inputs_event = torch.cuda.Event()
+        if rgb.device.type == "cpu":
+            torch.cuda.current_stream().wait_event(self._h2d["up"][self._h2d["idx"]])
+        self._inputs_event.record()                      # every read of the caller's tensors is enqueued before this point
         sample = {"RGB_im": st["RGB_im"], "rot": st["rot"], "trans": st["trans"], "new_traj": [nt]}
         cam = {"f": st["f"], "c": st["c"]}
         key = (nt, self._parity())
