@@ -255,6 +255,11 @@ int m4d_camera_pyramid(const float* cam_f, const float* cam_c, int b, int nlevel
 
 /* fill(n floats) on the stream (state reset: depth_prev_t <- 1000, m4depth_network.py:209) */
 int m4d_fill(float* p, int64_t n, float value, void* stream);
+/* x [b,h,w,c] (pixel stride x_pix_stride floats) -> the interior of y, a dense [b,h+shift_y,w+shift_x,c] tensor the caller zeroed
+ * once, at offset (shift_y, shift_x).  Keras Conv2D(strides=2, padding='same') pads an ODD dimension one pixel on BOTH sides
+ * (m4depth_network.py:66-72, SURVEY A.13: 15 -> 8); shifted by one pixel it is the even-sized problem (pad 0 / 1) that the
+ * tensor-core stride-2 convolution handles.  c % 4 == 0. */
+int m4d_pad_shift(const float* x, int x_pix_stride, int b, int h, int w, int c, int shift_y, int shift_x, float* y, void* stream);
 
 /* ---- metrics (metrics.py:1-64 + clipping m4depth_network.py:465-467) ----------------------------
  * gt, est [n] -> out[7] = AbsRel, SqRel, RMSE, RMSE_log, Delta1, Delta2, Delta3 for this batch

@@ -65,6 +65,7 @@ SIGNATURES = {
     "m4d_level_epilogue": (_i, [_p, _i, _p, _i, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "m4d_camera_pyramid": (_i, [_p, _p, _i, _i, _p, _p, _p]),
     "m4d_fill": (_i, [_p, _i64, _f, _p]),
+    "m4d_pad_shift": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "m4d_depth_metrics": (_i, [_p, _p, _i64, _f, _p, _p, _p]),
 }
 

@@ -134,8 +134,19 @@ class _Conv2D:
             tc_ok = False           # TMA needs 16-byte aligned bases and pixel strides
             _note_fallback("unaligned view", x.shape)
         if tc_ok and self.strides == 2 and not (h % 2 == 0 and w % 2 == 0 and xs == cin):
-            tc_ok = False           # the 2x2-cell formulation: even sizes (TF SAME pads bottom / right only), dense pixels
-            _note_fallback("stride 2 on an odd-sized or strided input", x.shape)
+            # The 2x2-cell formulation needs even sizes (TF SAME then pads bottom / right only) and dense pixels.  An odd
+            # dimension is padded one pixel on both sides: shifted by one pixel into a zeroed even-sized buffer it is the even case.
+            if cin % 4 == 0 and algo != 1:
+                sy, sx = h % 2, w % 2
+                key = ("pad", b, h, w)
+                pad = self._out.get(key)
+                if pad is None:
+                    pad = self._out[key] = torch.zeros(b, h + sy, w + sx, cin, dtype=torch.float32, device=x.device)
+                L.check(L.lib.m4d_pad_shift(L.ptr(x), xs, b, h, w, cin, sy, sx, L.ptr(pad), L.stream()))
+                x, h, w, xs = pad, h + sy, w + sx, cin
+            else:
+                tc_ok = False
+                _note_fallback("stride 2 on a strided input with cin % 4 != 0", x.shape)
         if algo != 1 and tc_ok:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -1384,3 +1384,30 @@ def test_inputs_consumed_event_orders_host_buffer_reuse():
         for k in buf:
             buf[k].fill_(float("nan"))                     # the loader reuses the buffers immediately
         assert torch.equal(out["depth"].cpu(), want[t])
+
+
+@pytest.mark.parametrize("cfg", [(1, 15, 20, 128, 192), (2, 33, 47, 64, 96), (1, 30, 41, 96, 128), (2, 7, 9, 16, 32)])
+def test_stride2_conv_on_odd_sizes_runs_on_the_tensor_cores(cfg):
+    """Keras Conv2D(strides=2, 'same') on an odd dimension pads one pixel on both sides (BASELINE configs[4]: 15 -> 8
+    at level 6).  The layer shifts the input into a zeroed even-sized buffer (m4d_pad_shift) and runs the tcgen05 stride-2
+    kernel: same results as the oracle convolution, and no FFMA2 fallback is recorded."""
+    m = _m4d()
+    from m4depth_b200 import m4depth_network as net
+    b, h, w, cin, cout = cfg
+    g = torch.Generator().manual_seed(h * w + cin)
+    x = torch.randn(b, h, w, cin, generator=g)
+    k = torch.randn(3, 3, cin, cout, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    want = oracle.leaky_relu(oracle.conv2d_same(x, k, bias, 2))
+    layer = net._Conv2D(cout, 2)
+    layer.assign(k, bias, "cuda")
+    assert layer.packed is not None
+    before = dict(net.conv_fallbacks)
+    got = layer(cu(x), alpha=0.1)
+    assert dict(net.conv_fallbacks) == before
+    assert tuple(got.shape) == tuple(want.shape)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-5 * float(want.abs().max()))
+    # twice through the same layer: the zero border of the padded buffer is never written
+    got2 = layer(cu(x * 2.0), alpha=0.1)
+    np.testing.assert_allclose(got2.cpu().numpy(), oracle.leaky_relu(oracle.conv2d_same(x * 2.0, k, bias, 2)).numpy(), rtol=1e-5,
+                               atol=1e-5 * float(want.abs().max()) * 2)
