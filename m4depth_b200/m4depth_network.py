@@ -597,6 +597,10 @@ class M4Depth:
         traj_samples, camera = data[0], data[1]
         self.step_counter += 1
         if not (self.use_cuda_graph and len(traj_samples) == 1):
+            # eager path (several frames per call, or graphs off): host tensors (e.g. dataloader samples) are uploaded here
+            dev = lambda t: t.to(self.device, non_blocking=True) if isinstance(t, torch.Tensor) and t.device.type == "cpu" else t
+            traj_samples = [{k: (v if k == "new_traj" else dev(v)) for k, v in s.items()} for s in traj_samples]
+            camera = {k: dev(v) for k, v in camera.items()}
             self._forward(traj_samples, camera)
             if self._inputs_event is None:
                 self._inputs_event = torch.cuda.Event()
