@@ -82,7 +82,7 @@ int main(int argc, char** argv) {
   a.cv_stride = xs; a.pd_stride = 0; a.cl_stride = xs; a.cl_scale = 0.5f; a.npix = (int64_t)npix;
   a.one = 1.f; a.neg_one = -1.f; a.neg_zero = -0.f;
   sa.tiles_x = (w + Cfg::TW - 1) / Cfg::TW; sa.tiles_y = (h + Cfg::TH - 1) / Cfg::TH; sa.n_tiles = sa.tiles_x * sa.tiles_y * b;
-  sa.cv_vec2 = 1; sa.pl_bulk = 1;
+  sa.cv_vec2 = 1; sa.pl_bulk = 1; sa.l2_prefetch = argc > 3 ? atoi(argv[3]) : 1;
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const int grid = std::min(sa.n_tiles, sms * cps);
