@@ -13,7 +13,9 @@ TF op, no autograd, no fused multiply-add across ops), of
 * ``m4depth_network.py:24-369``                 (DomainNormalization ... M4Depth.call)
 * ``metrics.py:1-64``
 
-PARITY PIN.  The reference ships no tests and no golden vectors, and TensorFlow is not
+PARITY PIN.  ``oracle/_ref/libbackproject_ref.so`` (``oracle/ref_binary.py``) is the reference's own BackProject CUDA source
+compiled unmodified: the oracle of the BackProject op and of the BP_FMA warp inside the fused PSCV (GPU tests).  For everything
+else: the reference ships no tests and no golden vectors, and TensorFlow is not
 installed in the build image nor on the GPU box, so the reference cannot be executed as-is.
 The pin used instead: ``tools/gen_golden.py`` imports the reference's *own, unmodified*
 ``utils/depth_operations.py`` / ``utils/dense_image_warp.py`` / ``m4depth_network.py`` from
