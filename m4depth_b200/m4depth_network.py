@@ -478,6 +478,7 @@ class M4Depth:
         self._out = None
         self._h2d = None            # side-stream upload state for host (CPU) frames
         self._inputs_event = None   # see inputs_consumed()
+        self._fetch = None          # see fetch_depth()
 
     # ------------------------------------------------------------------------------------------ weights
     def weight_layers(self):
@@ -576,6 +577,29 @@ class M4Depth:
 
     def _parity(self):
         return self.d_estimator.levels[0]._parity if self.d_estimator.levels[0].shape else 0
+
+    def fetch_depth(self, host_out):
+        """Asynchronous read-back of the latest depth map into a pinned host tensor ``[b,H,W,1]``; returns the CUDA event that
+        marks the copy done.  The map is first copied into a device staging buffer on the calling stream (a 16 MB device copy:
+        microseconds), and the PCIe transfer runs from there on a side stream - so the next ``call`` (which overwrites the
+        output buffer) does not wait for the transfer, only the next ``fetch_depth`` does."""
+        with torch.cuda.device(self.device):
+            if self._out is None:
+                raise L.M4DError("fetch_depth: no frame has been processed yet")
+            if self._fetch is None or tuple(self._fetch["stage"].shape) != tuple(self._out.shape):
+                self._fetch = {"stage": torch.empty_like(self._out), "stream": torch.cuda.Stream(device=self.device),
+                               "done": torch.cuda.Event(), "ready": torch.cuda.Event()}
+                self._fetch["done"].record()
+            f = self._fetch
+            main = torch.cuda.current_stream()
+            main.wait_event(f["done"])                       # the previous transfer has left the staging buffer
+            f["stage"].copy_(self._out, non_blocking=True)
+            f["ready"].record()
+            f["stream"].wait_event(f["ready"])
+            with torch.cuda.stream(f["stream"]):
+                host_out.copy_(f["stage"], non_blocking=True)
+                f["done"].record()
+            return f["done"]
 
     def inputs_consumed(self):
         """CUDA event recorded after the last asynchronous read of the caller's input tensors by the most recent ``call``.

@@ -1411,3 +1411,23 @@ def test_stride2_conv_on_odd_sizes_runs_on_the_tensor_cores(cfg):
     got2 = layer(cu(x * 2.0), alpha=0.1)
     np.testing.assert_allclose(got2.cpu().numpy(), oracle.leaky_relu(oracle.conv2d_same(x * 2.0, k, bias, 2)).numpy(), rtol=1e-5,
                                atol=1e-5 * float(want.abs().max()) * 2)
+
+
+def test_fetch_depth_overlaps_the_next_frame_without_tearing():
+    """M4Depth.fetch_depth: the depth map of frame t read into pinned host memory while frame t+1 is already running must be
+    frame t's map, bit for bit (it leaves through a device staging buffer, not the live output buffer)."""
+    m = _m4d()
+    frames, cam = _synth().synth_sequence(6, 2, 128, 192, "kitti", seed=9)
+    w = oracle.init_weights(6, seed=1, bias_std=0.05, dn_random=True)
+    want = _gpu_sequence(m, frames, cam, 6, weights=w)
+    model = m.M4Depth(nbre_levels=6, use_cuda_graph=True)
+    model.load_weights(w)
+    dcam = dev_cam(cam)
+    hosts = [torch.empty(2, 128, 192, 1).pin_memory() for _ in frames]
+    events = []
+    for t, fr in enumerate(frames):
+        model([[{"RGB_im": cu(fr["RGB_im"]), "rot": cu(fr["rot"]), "trans": cu(fr["trans"]), "new_traj": [t == 0] * 2}], dcam])
+        events.append(model.fetch_depth(hosts[t]))           # no synchronisation: the next frame is enqueued right behind
+    for t, ev in enumerate(events):
+        ev.synchronize()
+        assert torch.equal(hosts[t], want[t])
