@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm4d.so")
+# M4D_LIB: another build of the same library (A/B timing of kernel variants on the GPU box); default = the in-tree build
+LIB_PATH = os.environ.get("M4D_LIB") or os.path.join(_HERE, "libm4d.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -178,6 +179,35 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// The same MMAs with each shared-memory descriptor passed as its two 32-bit words.  The high word (stride between 8-row
+// groups, version, swizzle mode) is a constant of the kernel and only the 14-bit address field of the low word moves, so the
+// stride-1 issue path keeps one running low word per operand and adds compile-time tap / k-step offsets to it: one uniform
+// 32-bit add per descriptor instead of a 64-bit add in vector registers plus two R2UR moves (the issuer's instruction
+// stream, not the tensor pipe, paced every layer with N <= 64: profiles/r1n_conv_role_timers.md).
+template <bool HALF_, bool ACC>
+__device__ __forceinline__ void tc_mma_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  // (enable-input-d is a predicate operand: a compile-time constant here, folded by ptxas)
+#define M4D_MMA_W(KIND)                                                                                              \
+  asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .b32 t;\n\t.reg .pred p;\n\t"                                      \
+               "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tmov.b32 t, %6;\n\tsetp.ne.b32 p, t, 0;\n\t"        \
+               "tcgen05.mma.cta_group::1.kind::" KIND " [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),                      \
+               "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0)                               \
+               : "memory")
+  if (HALF_) M4D_MMA_W("f16");
+  else M4D_MMA_W("tf32");
+#undef M4D_MMA_W
+}
+template <bool HALF_, bool ACC>
+__device__ __forceinline__ void tc_mma_d(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+#define M4D_MMA_D(KIND)                                                                                              \
+  asm volatile("{\n\t.reg .b32 t;\n\t.reg .pred p;\n\tmov.b32 t, %4;\n\tsetp.ne.b32 p, t, 0;\n\t"                   \
+               "tcgen05.mma.cta_group::1.kind::" KIND " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),                      \
+               "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC ? 1 : 0)                                                   \
+               : "memory")
+  if (HALF_) M4D_MMA_D("f16");
+  else M4D_MMA_D("tf32");
+#undef M4D_MMA_D
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address and the byte
 // stride between 8-row groups in 16-byte units, LBO = 1 (unused for swizzled K-major), version 1, layout type 2.
@@ -391,6 +421,100 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const KbTaps tp = kb_taps<S2D, KS>(a, kb);
         const int kx_hi = tp.kx_hi();
         const int ntap = kx_hi - (S2D ? 1 : 0) + 1;                     // taps per window row that carry weights
+        if (!S2D) {
+          // Stride 1: all nine taps carry weights, so the three window rows are unrolled and every tap / k-step offset is a
+          // compile-time constant added to the running low word of a descriptor (tc_mma_w).  Per MMA the elected lane then
+          // executes a few uniform adds instead of ~9 vector / R2UR instructions.
+          constexpr uint32_t A_HI_W = HALF ? (((HALO_W * 64u) >> 4) | (1u << 14) | (4u << 29)) : (((HALO_W * 128u) >> 4) | (1u << 14) | (2u << 29));
+          constexpr uint32_t B_HI_W = HALF ? ((512u >> 4) | (1u << 14) | (4u << 29)) : ((1024u >> 4) | (1u << 14) | (2u << 29));
+          const uint32_t a_plane0 = sA + sa * A_STAGE + (HALF ? (uint32_t)A_SLOT : 0u);
+          const uint32_t aw_hi = ((a_plane0 >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t aw_lo = aw_hi + ((HALF ? (uint32_t)AH_PLANE : (uint32_t)A_SLOT) >> 4);
+          const uint32_t bw0 = ((sB >> 4) & 0x3FFFu) | (1u << 16);
+          const uint32_t bslab16 = b_stage_bytes >> 4;
+          const int nk = tp.nks;
+          // FULLK: every k-step of the k-block holds input channels (all but the last k-block of a layer whose channel count is
+          // not a multiple of 32): straight-line code, no per-k-step test inside the elected region
+          // the MMAs of one tap (ky, kx) against the weight slab in ring / resident slot `slab`
+          auto tap_mmas = [&](auto fullk, int ky, int kx, int slab) {
+            constexpr bool FULLK = decltype(fullk)::value;
+            const uint32_t tap16 = ((uint32_t)(ky * HALO_W + kx) * ROWB) >> 4;
+            const uint32_t bw = bw0 + (uint32_t)slab * bslab16;
+#pragma unroll
+            for (int ks = 0; ks < KC / KS; ++ks) {
+              if (FULLK || ks < nk) {
+                const uint32_t a_hi = aw_hi + tap16 + ks * 2, a_lo = aw_lo + tap16 + ks * 2;
+                const uint32_t b_hi = bw + ks * 2, b_lo = b_hi + lo_off16;
+                if (ky == 0 && kx == 0 && ks == 0) {
+                  tc_mma_w<HALF, false>(d_set, a_hi, A_HI_W, b_hi, B_HI_W, CONCAT ? idesc2 : idesc);
+                  tc_mma_w<HALF, false>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);
+                } else {
+                  tc_mma_w<HALF, true>(d_set, a_hi, A_HI_W, b_hi, B_HI_W, CONCAT ? idesc2 : idesc);
+                  tc_mma_w<HALF, true>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);
+                }
+                if (!CONCAT) tc_mma_w<HALF, true>(d_corr, a_hi, A_HI_W, b_lo, B_HI_W, idesc);
+              }
+            }
+          };
+          // weights through the ring (or resident but still landing: the CTA's first tile): one elected region per window
+          // row, after the waits for its three slabs
+          auto issue_rows = [&](auto fullk) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              int sbs[3];
+              {
+                PROF_BEGIN(i_wait_b);
+                int s_ = sb;
+                uint32_t ph_ = bph;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                  sbs[j] = s_;
+                  if (need_wgt_wait) mbar_wait(b_full + 8 * s_, ph_ & ring_mask);
+                  if (++s_ == NB) { s_ = 0; ph_ ^= 1u; }
+                }
+                sb = s_;
+                bph = ph_;
+                PROF_END(i_wait_b);
+              }
+              PROF_BEGIN(i_issue);
+              if (elect_one()) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  tap_mmas(fullk, ky, kx, sbs[kx]);
+                  if (!a.b_resident) tc_commit(b_empty + 8 * sbs[kx]);    // resident slabs are never released
+                }
+                if (ky == 2) {
+                  tc_commit(a_empty + 8 * sa);
+                  tc_commit(acc_full + 8 * set);
+                }
+              }
+              __syncwarp();
+              PROF_END(i_issue);
+            }
+          };
+          // resident weights, landed for good: nothing to wait for, the whole k-block is ONE elected region of straight-line
+          // code (slab = k-block * 9 + tap, no ring arithmetic)
+          auto issue_block = [&](auto fullk) {
+            PROF_BEGIN(i_issue);
+            const int sb0 = sb;
+            sb += 9;
+            if (elect_one()) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) tap_mmas(fullk, t / 3, t % 3, sb0 + t);
+              tc_commit(a_empty + 8 * sa);
+              tc_commit(acc_full + 8 * set);
+            }
+            __syncwarp();
+            PROF_END(i_issue);
+          };
+          if (need_wgt_wait) {
+            if (nk == KC / KS) issue_rows(std::true_type());
+            else issue_rows(std::false_type());
+          } else {
+            if (nk == KC / KS) issue_block(std::true_type());
+            else issue_block(std::false_type());
+          }
+        } else
 #pragma unroll 1
         for (int ky = tp.ky_lo; ky <= tp.ky_hi; ++ky) {
           // One elected region per window ROW (up to three taps): the per-region cost - barrier polls, election, moving

@@ -283,6 +283,8 @@ class DepthEstimatorLevel:
         self.interp = L.INTERP_GATHER
         self.shape = None
         self.trace = None           # optional dict: tests set it to {} to receive clones of intermediates
+        self._prepared = None       # set by prepare(): {"done": event, "sncv": bool}, consumed by the next call
+        self._prep_event = None
         self.pscv_events = None     # optional list: receives (start, end) CUDA events around the PSCV launch
 
     # ---- state variables, as in the reference (:160-163)
@@ -322,6 +324,34 @@ class DepthEstimatorLevel:
         self._para, self._depth, self._other = e(b, h, w, 1), e(b, h, w, 1), e(b, h, w, 4)
         self._prev_norm = None
 
+    def prepare(self, curr_f_maps, with_sncv):
+        """The part of ``call`` that depends on the encoder output only (:172-189 feature preparation and, when
+        ``with_sncv``, the :232 SNCV into the refiner-input buffer), enqueued on the CURRENT stream; the next ``call`` of
+        this level waits for it.  DepthEstimatorPyramid runs it for every level on a side stream, so that this
+        bandwidth-bound work overlaps the coarse levels, whose small launches leave most of the SMs idle."""
+        L.f32c(curr_f_maps, "curr_f_maps")
+        if self.shape is None:
+            self.build(curr_f_maps.shape, curr_f_maps.device)
+        if tuple(curr_f_maps.shape) != self.shape:
+            raise L.M4DError(f"level {self.lvl_depth} was built for {self.shape}, got {tuple(curr_f_maps.shape)} "
+                             "(static shapes, like the reference's state variables)")
+        b, h, w, c = self.shape
+        cuts, st = self.nbre_cuts, L.stream()
+        cur = self._f[self._parity]
+        if self.ablation.normalize_features:
+            L.check(L.lib.m4d_group_l2norm(L.ptr(curr_f_maps), b * h * w, c, cuts, L.ptr(cur), st))
+        else:
+            cur.copy_(curr_f_maps)
+        sncv = bool(with_sncv and self.ch_sncv >= 0)
+        if sncv:
+            with _nvtx("cost_volume"):
+                L.check(L.lib.m4d_sncv_fwd(L.ptr(cur), L.ptr(cur), b, h, w, c, cuts, 3,
+                                           self._x_in.data_ptr() + 4 * self.ch_sncv, self.xs, st))
+        if self._prep_event is None:
+            self._prep_event = torch.cuda.Event()
+        self._prep_event.record()
+        self._prepared = {"done": self._prep_event, "sncv": sncv}
+
     def call(self, curr_f_maps, prev_l_est, rot, trans, camera, new_traj, prev_f_maps=None, prev_t_depth=None):
         L.f32c(curr_f_maps, "curr_f_maps")
         if self.shape is None:
@@ -335,18 +365,25 @@ class DepthEstimatorLevel:
         cam_f, cam_c = L.f32c(camera["f"], "camera['f']"), L.f32c(camera["c"], "camera['c']")
         rd = rot.shape[1]
         cur = self._f[self._parity]
+        prepared, self._prepared = self._prepared, None
+        if prepared is not None:
+            # prepare() ran on the pyramid's side stream: everything below that reads `cur` or the SNCV channels waits for it
+            torch.cuda.current_stream().wait_event(prepared["done"])
 
         # :172-189 feature preparation
-        if self.ablation.normalize_features:
+        if prepared is not None:
+            pass
+        elif self.ablation.normalize_features:
             L.check(L.lib.m4d_group_l2norm(L.ptr(curr_f_maps), b * h * w, c, cuts, L.ptr(cur), st))
+        else:
+            cur.copy_(curr_f_maps)
+        if self.ablation.normalize_features:
             if prev_f_maps is not None:
                 if self._prev_norm is None:
                     self._prev_norm = torch.empty_like(cur)
                 L.check(L.lib.m4d_group_l2norm(L.ptr(L.f32c(prev_f_maps, "prev_f_maps")), b * h * w, c, cuts,
                                                L.ptr(self._prev_norm), st))
                 prev_f_maps = self._prev_norm
-        else:
-            cur.copy_(curr_f_maps)
 
         # :191-194 recurrent state
         if prev_f_maps is None and prev_t_depth is None:
@@ -392,7 +429,7 @@ class DepthEstimatorLevel:
             ev1.record()
             self.pscv_events.append((ev0, ev1))
         # :232 SNCV
-        if self.ch_sncv >= 0:
+        if self.ch_sncv >= 0 and not (prepared is not None and prepared["sncv"]):
             with _nvtx("cost_volume"):                              # m4depth_network.py:232
                 L.check(L.lib.m4d_sncv_fwd(L.ptr(cur), L.ptr(cur), b, h, w, c, cuts, 3,
                                            self._x_in.data_ptr() + 4 * self.ch_sncv, self.xs, st))
@@ -422,6 +459,9 @@ class DepthEstimatorPyramid:
                        for i in range(settings["nbre_lvls"])]
         self.is_training = settings["is_training"]
         self._cam = None
+        self.side_stream_prep = os.environ.get("M4D_SIDE_STREAM", "1") != "0"
+        self._side = None
+        self._fork = None
 
     def call(self, f_maps_pyrs, traj_samples, camera, training=False):
         if training:
@@ -438,6 +478,22 @@ class DepthEstimatorPyramid:
         for f_pyr_curr, sample in zip(f_maps_pyrs, traj_samples):
             rot, trans, new_traj = sample['rot'], sample['trans'], sample["new_traj"]
             d_est_curr = None
+            if self.side_stream_prep:
+                # Feature preparation and SNCV of every level depend on the encoder output only: fork them onto a side stream,
+                # coarse level first (the order the decoder needs them in).  Levels 6-3 are chains of small launches that leave
+                # most SMs idle; the bandwidth-bound preparation of levels 1-2 runs underneath them.  Each level's call waits
+                # for its own event, so the result is the same computation (same kernels, same buffers).  Works eagerly and
+                # under CUDA-graph capture (the fork / join events become graph dependencies).
+                is_new = _new_traj_flag(new_traj)
+                main = torch.cuda.current_stream()
+                if self._side is None or self._side.device != f_pyr_curr[0].device:
+                    self._side = torch.cuda.Stream(device=f_pyr_curr[0].device)
+                    self._fork = torch.cuda.Event()
+                self._fork.record(main)
+                self._side.wait_event(self._fork)
+                with torch.cuda.stream(self._side):
+                    for l in range(nl - 1, -1, -1):
+                        self.levels[l].prepare(f_pyr_curr[l], with_sncv=not is_new)
             for l in range(nl - 1, -1, -1):                                 # coarse -> fine (:293)
                 level = self.levels[l]
                 local_camera = {"f": self._cam[0][l], "c": self._cam[1][l]}

@@ -1189,6 +1189,45 @@ def test_model_streaming_graph_equals_eager():
     assert float(outs[True][0].min()) == 1000.0        # frame 0 is the new-trajectory pass-through
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_model_side_stream_preparation_is_the_same_computation(graph):
+    """DepthEstimatorPyramid forks the feature preparation and SNCV of every level onto a side stream (they depend on the encoder
+    output only): depth maps and every level's state are bit-identical to the serial order, eagerly and under CUDA graphs,
+    across a trajectory reset, and with ablations that remove the SNCV / the normalisation."""
+    m = _m4d()
+    nl, b, H, W = 6, 2, 128, 192
+    w = oracle.init_weights(nl, seed=3, bias_std=0.05, dn_random=True)
+    cam = dev_cam(camera_for("kitti", b, H, W))
+    for abl in (None, m.M4depthAblationParameters(SNCV=False), m.M4depthAblationParameters(normalize_features=False)):
+        outs = {}
+        for side in (False, True):
+            model = m.M4Depth(nbre_levels=nl, use_cuda_graph=graph, ablation_settings=abl)
+            model.d_estimator.side_stream_prep = side
+            wts = dict(w)
+            if abl is not None:       # the first refiner kernel's input width follows the switches (m4depth_network.py:223-242)
+                for lvl in range(1, nl + 1):
+                    cuts = 2 ** (lvl // 2)
+                    cin = 9 * cuts + 1 + 4 + (49 * cuts if abl.SNCV else 0) + 1
+                    gk = torch.Generator().manual_seed(100 + lvl)
+                    wts[f"d_estimator/levels/{lvl - 1}/disp_refiner/prep_conv_layers/0/kernel"] = \
+                        torch.randn(3, 3, cin, 128, generator=gk) * (2.0 / (9 * cin)) ** 0.5
+            model.load_weights(wts)
+            gg = torch.Generator().manual_seed(31)
+            res = []
+            for t in range(8):
+                rot, trans = motion(gg, b)
+                rgb = torch.rand(b, H, W, 3, generator=gg)
+                s = {"RGB_im": cu(rgb), "rot": cu(rot), "trans": cu(trans), "new_traj": [t in (0, 4)] * b}
+                res.append(model([[s], cam])["depth"].clone())
+            torch.cuda.synchronize()
+            res += [lvl.depth_prev_t.clone() for lvl in model.d_estimator.levels]
+            res += [lvl.prev_f_maps.clone() for lvl in model.d_estimator.levels]
+            outs[side] = res
+        for a, bb in zip(outs[False], outs[True]):
+            assert torch.equal(a, bb)
+
+
 # ----------------------------------------------------- whole model at the BASELINE.json sizes, bounded by oracle-vs-oracle
 def _synth():
     import sys
