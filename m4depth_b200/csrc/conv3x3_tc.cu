@@ -286,17 +286,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t sBar = sB + (uint32_t)a.nb * b_stage_bytes;
   const uint32_t a_full = sBar, a_ready = sBar + 8 * MAX_A_STAGES, a_empty = sBar + 16 * MAX_A_STAGES;
   const uint32_t b_full = sBar + 24 * MAX_A_STAGES, b_empty = b_full + 8 * MAX_B_STAGES;
-  const uint32_t acc_full = b_empty + 8 * MAX_B_STAGES, acc_empty = acc_full + 16;
+  const uint32_t acc_full = b_empty + 8 * MAX_B_STAGES, acc_empty = acc_full + 32;   // acc_full: [set][epilogue group]
   const uint32_t tmem_slot = acc_empty + 16;
   const uint32_t s_max = tmem_slot + 16;                                      // [MAX_A_STAGES (4 slots)] uint: max |x| bits of the landed halo
   const uint32_t s_scale = s_max + 16;                                        // [8] float: 1 / (s_x * s_w) of k-block ka & 7 (8 slots: the splitters run up to 3 k-blocks ahead of the MMAs, the epilogue one behind)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = a.kblocks, NB = a.nb, NA = a.na;
-  // Up to 64 output channels one epilogue group (warps 8-11) owns both 32-column chunks and the other four warps (12-15)
-  // join the splitters: with few columns per MMA the split, not the tensor pipe, paces a k-block.
-  const bool wide_split = a.cout <= 64;
-  const uint32_t nsplit = wide_split ? 256u : 128u;
+  // Up to 64 output channels ("thin") an epilogue group owns both 32-column chunks of a tile and the two groups take
+  // ALTERNATE tiles: with few columns the MMAs of a tile are short, and one group's chain per tile (accumulator wait, TMEM
+  // read-out, bias, staging tile, TMA store: ~2800 clocks, profiles/r1n_conv_role_timers.md) was longer than the tile's MMAs
+  // and set the pace of the 32->16 / 16->5 class of layers.  Every mbarrier keeps exactly one waiting role: the issuer commits
+  // a tile's accumulators to the acc_full barrier of the group that owns the tile.
+  const bool thin = a.cout <= 64;
+  constexpr uint32_t nsplit = 128u;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
@@ -309,10 +312,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(b_full + 8 * s, 1);
       mbar_init(b_empty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, wide_split ? 4 : 8);   // one lane of each epilogue warp
-    }
+    for (int s = 0; s < 4; ++s) mbar_init(acc_full + 8 * s, 1);
+    for (int s = 0; s < 2; ++s) mbar_init(acc_empty + 8 * s, thin ? 4 : 8);   // one lane of each warp that drains the set
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < 4; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
   }
@@ -400,8 +401,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     int ka = 0, sb = 0, sa = 0;
     uint32_t bph = 0, aph = 0;
     const uint32_t ring_mask = a.b_resident ? 0u : 1u;               // resident weights: every slab's barrier completed phase 0 for good
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    int it = 0;
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
       if (a.b_resident) sb = 0;                                      // slab = position within the tile
+      const uint32_t grp_off = thin ? 8u * (uint32_t)(it & 1) : 0u;  // epilogue group that owns this tile
       const bool need_wgt_wait = !a.b_resident || item == (int)blockIdx.x;   // resident slabs: landed for good after the first tile
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
@@ -485,7 +488,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 }
                 if (ky == 2) {
                   tc_commit(a_empty + 8 * sa);
-                  tc_commit(acc_full + 8 * set);
+                  tc_commit(acc_full + 16 * set + grp_off);
                 }
               }
               __syncwarp();
@@ -502,7 +505,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int t = 0; t < 9; ++t) tap_mmas(fullk, t / 3, t % 3, sb0 + t);
               tc_commit(a_empty + 8 * sa);
-              tc_commit(acc_full + 8 * set);
+              tc_commit(acc_full + 16 * set + grp_off);
             }
             __syncwarp();
             PROF_END(i_issue);
@@ -574,7 +577,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             }
             if (ky == tp.ky_hi) {
               tc_commit(a_empty + 8 * sa);
-              tc_commit(acc_full + 8 * set);
+              tc_commit(acc_full + 16 * set + grp_off);
             }
           }
           __syncwarp();
@@ -584,9 +587,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     PROF_WRITE(1, i_wait_acc); PROF_WRITE(2, i_wait_a); PROF_WRITE(3, i_wait_b); PROF_WRITE(4, i_issue);
-  } else if ((warp >= 4 && warp < 8) || (wide_split && warp >= 12)) {
+  } else if (warp >= 4 && warp < 8) {
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
-    const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
+    const int t = threadIdx.x - 128;
     const int NS = (int)nsplit;
     PROF_DECL(s_wait_full); PROF_DECL(s_split);
     // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
@@ -639,7 +642,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // needed before two k-blocks from now - is cleared, so one barrier per k-block suffices
           const uint32_t slot = s_max + 4 * (uint32_t)(ka & 3);
           if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(slot), "r"(mx) : "memory");
-          asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory");
+          asm volatile("bar.sync 3, %0;" ::"n"(nsplit) : "memory");
           uint32_t mbits;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(slot) : "memory");
           // s_x = 2^(14 - E) with E the exponent of the maximum (so max * s_x is in [2^14, 2^15)); exponents are clamped so that
@@ -681,20 +684,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         PROF_END(s_split);
       }
     if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); }
-  } else if (warp >= 8 && (!wide_split || warp < 12)) {
-    // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant, group g the
-    // 32-column chunks g and g+2.  After every k-block the group adds that k-block's accumulators into its register sums and
-    // hands the set back; after the last one it applies bias + leaky_relu and stores through its staging tile.
+  } else if (warp >= 8) {
+    // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant.  More than 64
+    // output channels: both groups work on every tile, group g on the 32-column chunks g and g+2.  Thin layers: group g owns
+    // the CTA's tiles with local index & 1 == g, both chunks.  After every k-block the group adds that k-block's accumulators
+    // into its register sums and hands the set back; after the last one it applies bias + leaky_relu and stores through its
+    // staging tile.
     const int grp = (warp - 8) >> 2, q = warp & 3;
     const int m = q * 32 + lane;
     const int et = threadIdx.x - 256 - grp * 128;                  // 0..127 within the group
-    // staging tiles for the TMA stores: one per group; with <= 64 output channels group 1 does not store, so group 0 alternates
-    // between both tiles and only waits for the store before the previous one to have read its tile
-    uint32_t nstore = 0;
+    // staging tiles for the TMA stores: one per group
     const int nchunks = (a.cout + 31) >> 5;
     PROF_DECL(e_wait_full); PROF_DECL(e_drain); PROF_DECL(e_final);
-    int ka = 0;
-    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
+    int ka = 0, it = 0;
+    uint32_t ph_full0 = 0u, ph_full1 = 0u;                         // phase of this group's acc_full barrier of either set
+    const uint32_t my_full = acc_full + (thin ? 8u * (uint32_t)grp : 0u);
+    for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
+      if (thin && (it & 1) != grp) { ka += KB; continue; }          // the other group's tile
       const int tile = item / a.nslices;
       const int n0 = (item - tile * a.nslices) * a.cout;
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
@@ -702,7 +708,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       float sum[2][32];
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int set = ka & 1;
-        { PROF_BEGIN(e_wait_full); mbar_wait(acc_full + 8 * set, (ka >> 1) & 1); PROF_END(e_wait_full); }
+        { PROF_BEGIN(e_wait_full); mbar_wait(my_full + 16 * set, set ? ph_full1 : ph_full0); PROF_END(e_wait_full); }
+        if (set) ph_full1 ^= 1u; else ph_full0 ^= 1u;
         PROF_BEGIN(e_drain);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)set * 256u;
@@ -711,7 +718,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const float inv_cross = inv_main * (1.0f / 2048.0f);
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
-          const int c0 = (wide_split ? ci : grp + 2 * ci) * 32;
+          const int c0 = (thin ? ci : grp + 2 * ci) * 32;
           if (c0 < a.cout) {
             const int nc = a.cout - c0 >= 32 ? 32 : 16;
             for (int jj = 0; jj < a.nacc; ++jj) {                   // hi*hi, then the cross-term accumulator(s)
@@ -731,7 +738,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty + 8 * set);            // all 8 epilogue warps arrive, with or without chunks
+        if (lane == 0) mbar_arrive(acc_empty + 8 * set);            // every warp that works on this tile arrives, with or without chunks
         PROF_END(e_drain);
       }
       PROF_BEGIN(e_final);
@@ -740,8 +747,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
-        const int c0 = (wide_split ? ci : grp + 2 * ci) * 32;
-        if ((wide_split ? ci : grp + 2 * ci) >= nchunks) continue;
+        const int c0 = (thin ? ci : grp + 2 * ci) * 32;
+        if ((thin ? ci : grp + 2 * ci) >= nchunks) continue;
         const int nc = a.cout - c0 >= 32 ? 32 : 16;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -750,12 +757,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
           // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
           // store has finished READING it.
-          const uint32_t sbuf = sOut + (wide_split ? (nstore & 1u) : (uint32_t)grp) * OUT_SLOT;
-          ++nstore;
-          if (et == 0) {
-            if (wide_split) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
+          const uint32_t sbuf = sOut + (uint32_t)grp * OUT_SLOT;
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll
