@@ -217,6 +217,14 @@ int m4d_debug_conv_profile(long long* device_buf);
 #define M4D_CONV_PREC_3XFP16 1
 int64_t m4d_conv3x3_tc_packed_floats_p(int cin, int cout, int stride, int prec);
 int m4d_conv3x3_tc_pack_p(const float* kernel_hwio, int cin, int cout, int stride, int prec, float* packed, void* stream);
+/* Flags that may be OR-ed into `slices` (bits 0-3 = the slice count above):
+ *   M4D_CONV_PDL                 launch with programmatic stream serialization: the kernel may be scheduled while the kernel
+ *                                before it in the stream is still draining (its set-up then overlaps that tail) and waits
+ *                                (griddepcontrol.wait) before it reads x or the weights - same results, same stream order.
+ *   M4D_CONV_PDL_WEIGHTS_STABLE  with M4D_CONV_PDL: `packed` and `bias` were complete before the preceding kernel was
+ *                                enqueued (true from a layer's second call on), so the weight loads need not wait. */
+#define M4D_CONV_PDL (1 << 8)
+#define M4D_CONV_PDL_WEIGHTS_STABLE (1 << 9)
 int m4d_conv3x3_tc_fwd_p(const float* x, int x_pix_stride, const float* packed, const float* bias, int b, int h, int w,
                          int cin, int cout, int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int slices,
                          void* stream);

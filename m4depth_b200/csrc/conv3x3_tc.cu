@@ -71,6 +71,8 @@ struct TcArgs {
   int concat;                       // Cout <= 64: hi*hi and hi*lo in ONE MMA of N = 2*Cout over the adjacent [hi|lo] weight planes
   int s2d_c;                        // 0: stride 1.  C > 0: stride-2 conv over C input channels as a 2x2-cell conv (see below)
   int s2d_chunks;                   // 32-channel chunks of one input row pair's (px, c) range = 2C / 32
+  int pdl;                          // launched with programmatic stream serialization: 1 = wait for the preceding grid before
+                                    // anything is read, 2 = the packed weights are older than the preceding grid: only x waits
   long long* prof;                  // M4D_TC_PROFILE builds: [grid][16] clock64 sums per role (else unused)
   const float* w_scale;             // 3xFP16 mode: 1 / (power-of-two scale the packed weights were multiplied by), device scalar
   float alpha;
@@ -293,6 +295,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = a.kblocks, NB = a.nb, NA = a.na;
+  // Programmatic dependent launch (a.pdl): the next kernel in the stream may be scheduled as soon as every CTA of this grid
+  // has passed this point, i.e. on SMs this grid leaves idle or frees early; its barrier set-up, TMEM allocation and weight
+  // loads then overlap this grid's tail instead of following it.  What a grid reads from its predecessor (x) - and what it
+  // overwrites (y: stored only after x has been read) - is ordered by griddepcontrol.wait in the A producer below.
+  if (a.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // Up to 64 output channels ("thin") an epilogue group owns both 32-column chunks of a tile and the two groups take
   // ALTERNATE tiles: with few columns the MMAs of a tile are short, and one group's chain per tile (accumulator wait, TMEM
   // read-out, bias, staging tile, TMA store: ~2800 clocks, profiles/r1n_conv_role_timers.md) was longer than the tile's MMAs
@@ -333,6 +340,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (warp == 0) {
     // ===== A producer
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // the preceding grid's writes (this layer's input) are visible
     PROF_DECL(a_wait_empty);
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
@@ -358,6 +366,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   } else if (warp == 1) {
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    if (a.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");  // weights possibly packed by the preceding grid
     int s = 0;                                                       // ring position and phase, advanced incrementally:
     uint32_t ph = 0;                                                 // (a run-time % and / per tap cost more than the tap's MMAs)
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
@@ -393,9 +402,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // fresh accumulators that the epilogue warps add in registers (round to nearest), and the small cross terms, whose
     // truncation errors are 2^-11 smaller, have their own accumulators.
     // Accumulator set (TMEM columns from d_set):  Cout > 64:  [hi*hi | lo*hi + hi*lo]           three MMAs per k-step
-    //                                             Cout <= 64: [hi*hi | hi*lo | lo*hi]           two MMAs per k-step: A_hi against
-    // the adjacent [W_hi ; W_lo] planes as one N = 2*Cout operand.  With small N the MMAs are bound by the 4 KB A-operand
-    // read from shared memory (128 B/clk), so one A pass less per k-step is 25-30 % of the layer.
+    //                                             concatenated: [hi*hi | hi*lo + lo*hi]         two MMAs per k-step: A_hi against
+    // the adjacent [W_hi ; W_lo] planes as ONE operand of N = 2*Cout columns (which leaves hi*lo right where the cross terms
+    // are collected), then A_lo x W_hi accumulated onto it.  Below 128 columns an MMA is bound by its operand reads from
+    // shared memory (4 KB of A per k-step at 128 B/clk against N/2 tensor clocks), so one A pass less per k-step is 10 %
+    // (N = 96) to 30 % (N <= 64) of the layer; at N = 128 it is the same tensor time in two instructions instead of three.
     const uint32_t ncol = (uint32_t)a.cout;
     PROF_DECL(i_wait_acc); PROF_DECL(i_wait_a); PROF_DECL(i_wait_b); PROF_DECL(i_issue);
     int ka = 0, sb = 0, sa = 0;
@@ -415,7 +426,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         // needs it (TMA writes and the splitters' fence.proxy.async'ed stores reach the tensor core through the mbarriers).
         tc_fence_after();
         const uint32_t d_set = tmem_base + (uint32_t)set * 256u;
-        const uint32_t d_corr = d_set + (CONCAT ? 2u : 1u) * ncol;
+        const uint32_t d_corr = d_set + ncol;            // cross terms: right behind hi*hi, where the concatenated MMA puts hi*lo
         { PROF_BEGIN(i_wait_a); mbar_wait(a_ready + 8 * sa, aph); PROF_END(i_wait_a); }
         // descriptors of this stage's hi / lo halo planes at tap (0,0), k-step 0; taps and k-steps add 16-byte units to the low word
         const uint64_t dA_hi = HALF ? umma_desc64(sA + sa * A_STAGE + A_SLOT, HALO_W * 64) : umma_desc(sA + sa * A_STAGE, HALO_W * 128);
@@ -450,7 +461,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint32_t b_hi = bw + ks * 2, b_lo = b_hi + lo_off16;
                 if (ky == 0 && kx == 0 && ks == 0) {
                   tc_mma_w<HALF, false>(d_set, a_hi, A_HI_W, b_hi, B_HI_W, CONCAT ? idesc2 : idesc);
-                  tc_mma_w<HALF, false>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);
+                  if (CONCAT) tc_mma_w<HALF, true>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);     // hi*lo is already there
+                  else tc_mma_w<HALF, false>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);
                 } else {
                   tc_mma_w<HALF, true>(d_set, a_hi, A_HI_W, b_hi, B_HI_W, CONCAT ? idesc2 : idesc);
                   tc_mma_w<HALF, true>(d_corr, a_lo, A_HI_W, b_hi, B_HI_W, idesc);
@@ -558,7 +570,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 if (HALF) {
                   if (CONCAT) {
                     tc_mma_f16(d_set, a_hi, b_hi, idesc2, acc);
-                    tc_mma_f16(d_corr, a_lo, b_hi, idesc, acc);
+                    tc_mma_f16(d_corr, a_lo, b_hi, idesc, 1u);
                   } else {
                     tc_mma_f16(d_set, a_hi, b_hi, idesc, acc);
                     tc_mma_f16(d_corr, a_lo, b_hi, idesc, acc);
@@ -566,7 +578,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                   }
                 } else if (CONCAT) {
                   tc_mma_tf32(d_set, a_hi, b_hi, idesc2, acc);
-                  tc_mma_tf32(d_corr, a_lo, b_hi, idesc, acc);
+                  tc_mma_tf32(d_corr, a_lo, b_hi, idesc, 1u);
                 } else {
                   tc_mma_tf32(d_set, a_hi, b_hi, idesc, acc);
                   tc_mma_tf32(d_corr, a_lo, b_hi, idesc, acc);
@@ -593,6 +605,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int NS = (int)nsplit;
     PROF_DECL(s_wait_full); PROF_DECL(s_split);
     // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
+    if (a.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     const float w_inv_scale = HALF ? __ldg(a.w_scale) : 1.f;
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x)
@@ -934,6 +947,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
               int stride, int prec, float leaky_alpha, float* y, int y_pix_stride, int force, cudaStream_t stream) {
   const bool half = prec == M4D_CONV_PREC_3XFP16;
   const int force_slices = force & 15, force_na = (force >> 4) & 3;      // tuning: slices | halo stages << 4
+  const int pdl = (force >> 8) & 3;       // M4D_CONV_PDL (1 << 8) [| M4D_CONV_PDL_WEIGHTS_STABLE (1 << 9)]: see include/m4d.h
   const float* w_scale = packed + tc_plane_floats(cin, cout, stride, prec);      // 3xFP16: 1 / s_w behind the planes
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
@@ -1007,6 +1021,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   }
   TcArgs a;
   a.prof = g_conv_prof;
+  a.pdl = pdl == 0 ? 0 : (pdl & 2 ? 2 : 1);
   a.bias = bias; a.y = y; a.h = oh; a.w = ow; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha; a.w_scale = w_scale;
   a.s2d_c = stride == 1 ? 0 : cin;
@@ -1018,10 +1033,10 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.nslices = nslices;
   a.nitems = a.ntiles * nslices;
   a.ctot = ctot;
-  // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block; a set is [hi*hi | hi*lo | lo*hi] (Cout <= 64,
-  // two MMAs per k-step) or [hi*hi | cross terms] (three MMAs per k-step).
-  a.concat = cout <= 64 ? 1 : 0;
-  a.nacc = a.concat ? 3 : 2;
+  // TMEM: 512 columns = 2 accumulator sets of 256 that alternate per k-block; a set is [hi*hi | cross terms].
+  // force bit 10 (tuning): three separate MMAs per k-step for N > 64 instead of the concatenated pair
+  a.concat = (cout <= 64 || !((force >> 10) & 1)) ? 1 : 0;
+  a.nacc = 2;
   a.nsets = 2;
   // halo stages: a k-block's chain TMA load -> split -> MMAs -> release is several thousand clocks of latency; with few
   // output channels the MMAs are short and two stages leave the tensor pipe waiting, so take a third where the weight
@@ -1072,7 +1087,26 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     attr_set.store(true, std::memory_order_release);
   }
   const int grid = a.nitems < m4d_sm_count() ? a.nitems : m4d_sm_count();
-  kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)]<<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+  KernelFn kern = kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)];
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mx, mw, my, a);
+    if (e != cudaSuccess) {
+      m4d_set_error("m4d_conv3x3_tc_fwd: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+      return M4D_ECUDA;
+    }
+  } else {
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+  }
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
 }

@@ -82,6 +82,8 @@ def _new_traj_flag(new_traj):
 # precision mode of the tensor-core convs (include/m4d.h M4D_CONV_PREC_*): 0 = 3xTF32, 1 = 3xFP16 (scaled fp16 hi/lo planes:
 # same error class, twice the tensor-core rate).  M4D_CONV_PREC in the environment overrides the default.
 DEFAULT_CONV_PREC = int(os.environ.get("M4D_CONV_PREC", "1"))
+CONV_PDL, CONV_PDL_WEIGHTS_STABLE = 1 << 8, 1 << 9
+USE_PDL = os.environ.get("M4D_CONV_PDL", "1") != "0"
 
 
 class _Conv2D:
@@ -96,6 +98,7 @@ class _Conv2D:
         self.events = None          # optional list: receives (start, end) CUDA events around the launch (bench.py roofline)
         self.bias = None            # [cout]
         self._out = {}
+        self._calls = 0             # tensor-core launches since the weights were (re)packed
 
     def assign(self, kernel, bias, device):
         k = kernel.to(device=device, dtype=torch.float32).contiguous()
@@ -103,6 +106,7 @@ class _Conv2D:
             raise L.M4DError(f"conv kernel must be [3,3,cin,{self.filters}], got {tuple(k.shape)}")
         self.kernel = k
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        self._calls = 0
         # tensor-core path (stride 1, or stride 2 with cin % 16 == 0; cout <= 256): TF32 hi/lo planes packed once per layer
         self.packed = None
         n = L.lib.m4d_conv3x3_tc_packed_floats_p(k.shape[2], self.filters, self.strides, self.prec)
@@ -151,8 +155,12 @@ class _Conv2D:
             if self.events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            # programmatic dependent launch (include/m4d.h M4D_CONV_PDL): from a layer's second call on its packed weights are
+            # older than whatever precedes the launch in the stream, so they may be fetched before the grid dependency resolves
+            flags = (CONV_PDL | (CONV_PDL_WEIGHTS_STABLE if self._calls > 0 else 0)) if USE_PDL else 0
+            self._calls += 1
             L.check(L.lib.m4d_conv3x3_tc_fwd_p(L.ptr(x), xs, L.ptr(self.packed), L.ptr(self.bias), b, h, w, cin, self.filters,
-                                               self.strides, self.prec, float(alpha), L.ptr(out), ys, int(slices), L.stream()))
+                                               self.strides, self.prec, float(alpha), L.ptr(out), ys, int(slices) | flags, L.stream()))
             if self.events is not None:
                 ev1.record()
                 self.events.append((ev0, ev1))
