@@ -169,6 +169,12 @@ int m4d_domain_norm(const float* x, int b, int h, int w, int c, const float* sca
  * kernel HWIO [3,3,3,16]; stats_ws: 2*b*16 doubles (need not be initialised); out [b,h,w,16], 16-byte aligned. */
 int m4d_rgb_conv_dn(const float* x, int x_pix_stride, const float* kernel_hwio, const float* conv_bias, int b, int h, int w,
                     const float* dn_scale, const float* dn_bias, float leaky_alpha, double* stats_ws, float* out, void* stream);
+/* The same call with the conv kernel [3,3,3,16] and its bias given as HOST pointers: they travel in the kernel parameter block
+ * and are read as constant operands of the FMAs (no shared-memory weight loads: ~2x faster than the call above, and faster
+ * than storing the conv output).  Same results bit for bit.  Everything else as above (x, DN parameters, workspace: device). */
+int m4d_rgb_conv_dn_hostw(const float* x, int x_pix_stride, const float* kernel_hwio_host, const float* conv_bias_host, int b, int h,
+                          int w, const float* dn_scale, const float* dn_bias, float leaky_alpha, double* stats_ws, float* out,
+                          void* stream);
 
 /* Keras Conv2D(3x3, padding='same') + bias + optional leaky_relu (:63-72,104-114; TF SAME padding rule).
  * x [b,h,w,cin] with row stride x_pix_stride (>= cin); kernel HWIO [3,3,cin,cout]; y [b,oh,ow,cout] with row

@@ -71,6 +71,7 @@ struct TcArgs {
   int concat;                       // Cout <= 64: hi*hi and hi*lo in ONE MMA of N = 2*Cout over the adjacent [hi|lo] weight planes
   int s2d_c;                        // 0: stride 1.  C > 0: stride-2 conv over C input channels as a 2x2-cell conv (see below)
   int s2d_chunks;                   // 32-channel chunks of one input row pair's (px, c) range = 2C / 32
+  int thin_mode;                    // cout <= 64: 1 = epilogue groups take alternate tiles, 4 splitter warps; 2 = one epilogue group, 8 splitter warps
   int pdl;                          // launched with programmatic stream serialization: 1 = wait for the preceding grid before
                                     // anything is read, 2 = the packed weights are older than the preceding grid: only x waits
   long long* prof;                  // M4D_TC_PROFILE builds: [grid][16] clock64 sums per role (else unused)
@@ -249,6 +250,23 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Two values of the 3xFP16 split: xs = x * s (s a power of two: exact), h1 = fp16(xs), h2 = fp16((xs - h1) * 2^11); both
+// differences and the 2^11 are exact, so the only roundings are the two conversions.  Seven instructions per pair: packed
+// FMUL2, F2FP pack, two mixed-precision FHADD (h1 - xs, fp16 operand read in place), packed FMUL2 by -2^11, F2FP pack.
+__device__ __forceinline__ void split_f16_pair(uint32_t x0, uint32_t x1, float s, uint32_t& h1, uint32_t& h2) {
+  unsigned long long p, q, d, e;
+  float a0, a1, d0, d1, e0, e1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "r"(x0), "r"(x1));
+  asm("{\n\t.reg .b64 s2;\n\tmov.b64 s2, {%2, %2};\n\tmul.rn.f32x2 %0, %1, s2;\n\t}" : "=l"(q) : "l"(p), "f"(s));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(q));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(a1), "f"(a0));
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.f16 %0, lo, %3;\n\tsub.rn.f32.f16 %1, hi, %4;\n\t}"
+      : "=f"(d0), "=f"(d1) : "r"(h1), "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("{\n\t.reg .b64 k2;\n\t.reg .f32 k;\n\tmov.f32 k, 0fC5000000;\n\tmov.b64 k2, {k, k};\n\tmul.rn.f32x2 %0, %1, k2;\n\t}" : "=l"(e) : "l"(d));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(e0), "=f"(e1) : "l"(e));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h2) : "f"(e1), "f"(e0));
+}
 // x = hi + lo with hi = x rounded to TF32 (10-bit mantissa, ties away); lo = x - hi is exact in fp32
 __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(__uint_as_float(x)));
@@ -305,8 +323,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   // read-out, bias, staging tile, TMA store: ~2800 clocks, profiles/r1n_conv_role_timers.md) was longer than the tile's MMAs
   // and set the pace of the 32->16 / 16->5 class of layers.  Every mbarrier keeps exactly one waiting role: the issuer commits
   // a tile's accumulators to the acc_full barrier of the group that owns the tile.
+  // (thin_mode 2, tuning: one epilogue group for every tile and warps 12-15 as four more splitter warps)
   const bool thin = a.cout <= 64;
-  constexpr uint32_t nsplit = 128u;
+  const bool alt = thin && a.thin_mode != 2;                       // epilogue groups alternate tiles
+  const bool split8 = thin && a.thin_mode == 2;
+  const uint32_t nsplit = split8 ? 256u : 128u;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   if (threadIdx.x == 0) {
@@ -320,7 +341,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_init(b_empty + 8 * s, 1);
     }
     for (int s = 0; s < 4; ++s) mbar_init(acc_full + 8 * s, 1);
-    for (int s = 0; s < 2; ++s) mbar_init(acc_empty + 8 * s, thin ? 4 : 8);   // one lane of each warp that drains the set
+    for (int s = 0; s < 2; ++s) mbar_init(acc_empty + 8 * s, thin ? 4 : 8);   // one lane of each warp that drains a tile's set
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int i = 0; i < 4; ++i) asm volatile("st.shared.u32 [%0], %1;" ::"r"(s_max + 4 * i), "r"(0u) : "memory");
   }
@@ -342,6 +363,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
     if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");      // the preceding grid's writes (this layer's input) are visible
     PROF_DECL(a_wait_empty);
+#ifdef M4D_TC_PROFILE
+    const long long prof_kernel_t0 = clock64();
+#endif
     int ka = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x) {
       const int tile = item / a.nslices;
@@ -363,6 +387,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     PROF_WRITE(0, a_wait_empty);
+#ifdef M4D_TC_PROFILE
+    if (a.prof && lane == 0) a.prof[(size_t)blockIdx.x * 16 + 10] = clock64() - prof_kernel_t0;   // the CTA's life in SM clocks
+#endif
   } else if (warp == 1) {
     // ===== B producer: both planes of one (k-block, tap) weight slab per load
     if (elect_one()) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -415,7 +442,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     int it = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
       if (a.b_resident) sb = 0;                                      // slab = position within the tile
-      const uint32_t grp_off = thin ? 8u * (uint32_t)(it & 1) : 0u;  // epilogue group that owns this tile
+      const uint32_t grp_off = alt ? 8u * (uint32_t)(it & 1) : 0u;   // epilogue group that owns this tile
       const bool need_wgt_wait = !a.b_resident || item == (int)blockIdx.x;   // resident slabs: landed for good after the first tile
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         // every k-block accumulates into a fresh accumulator set (ping-pong): the epilogue warps add the sets in registers
@@ -599,11 +626,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     PROF_WRITE(1, i_wait_acc); PROF_WRITE(2, i_wait_a); PROF_WRITE(3, i_wait_b); PROF_WRITE(4, i_issue);
-  } else if (warp >= 4 && warp < 8) {
+  } else if ((warp >= 4 && warp < 8) || (split8 && warp >= 12)) {
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
-    const int t = threadIdx.x - 128;
+    const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
     const int NS = (int)nsplit;
-    PROF_DECL(s_wait_full); PROF_DECL(s_split);
+    PROF_DECL(s_wait_full); PROF_DECL(s_split); PROF_DECL(s_bar); PROF_DECL(s_fence);
     // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
     if (a.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     const float w_inv_scale = HALF ? __ldg(a.w_scale) : 1.f;
@@ -635,7 +662,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           const int rem_ch = (S2D ? 4 * a.s2d_c : a.cin) - kb * KC;
           const int jmax = rem_ch >= KC ? 4 : (rem_ch + 15) / 16 * 2;
           uint4 va[UPT], vb[UPT];
-          uint32_t mx = 0u;
+          float mxf = 0.f;
 #pragma unroll
           for (int u = 0; u < UPT; ++u) {
             const int idx = t + u * NS;
@@ -644,18 +671,23 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               const uint32_t row = hi_p + (uint32_t)px * 128u;
               va[u] = lds128(row + (uint32_t)(((2 * j) ^ (px & 7)) * 16));
               vb[u] = lds128(row + (uint32_t)(((2 * j + 1) ^ (px & 7)) * 16));
-              mx = max(mx, max(max(va[u].x & 0x7FFFFFFFu, va[u].y & 0x7FFFFFFFu), max(va[u].z & 0x7FFFFFFFu, va[u].w & 0x7FFFFFFFu)));
-              mx = max(mx, max(max(vb[u].x & 0x7FFFFFFFu, vb[u].y & 0x7FFFFFFFu), max(vb[u].z & 0x7FFFFFFFu, vb[u].w & 0x7FFFFFFFu)));
+              // |x| is an operand modifier of FMNMX / FMNMX3: five instructions per eight values (NaNs are passed over)
+              const float m0 = fmaxf(fmaxf(fabsf(__uint_as_float(va[u].x)), fabsf(__uint_as_float(va[u].y))),
+                                     fmaxf(fabsf(__uint_as_float(va[u].z)), fabsf(__uint_as_float(va[u].w))));
+              const float m1 = fmaxf(fmaxf(fabsf(__uint_as_float(vb[u].x)), fabsf(__uint_as_float(vb[u].y))),
+                                     fmaxf(fabsf(__uint_as_float(vb[u].z)), fabsf(__uint_as_float(vb[u].w))));
+              mxf = fmaxf(mxf, fmaxf(m0, m1));
             }
           }
-          // largest magnitude of the k-block's halo (compared as the bits of |x|: monotonic for finite values)
+          // largest magnitude of the k-block's halo (from here on as the bits of |x|: monotonic for non-negative floats)
+          uint32_t mx = __float_as_uint(mxf);
 #pragma unroll
           for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
           // four slots in rotation: slot (ka & 3) collects this k-block's maximum, slot (ka + 2) & 3 - read two k-blocks ago, not
           // needed before two k-blocks from now - is cleared, so one barrier per k-block suffices
           const uint32_t slot = s_max + 4 * (uint32_t)(ka & 3);
           if (lane == 0) asm volatile("red.shared.max.u32 [%0], %1;" ::"r"(slot), "r"(mx) : "memory");
-          asm volatile("bar.sync 3, %0;" ::"n"(nsplit) : "memory");
+          { PROF_BEGIN(s_bar); asm volatile("bar.sync 3, %0;" ::"r"(nsplit) : "memory"); PROF_END(s_bar); }
           uint32_t mbits;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mbits) : "r"(slot) : "memory");
           // s_x = 2^(14 - E) with E the exponent of the maximum (so max * s_x is in [2^14, 2^15)); exponents are clamped so that
@@ -674,30 +706,24 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const int idx = t + u * NS;
             if (idx < NU && (idx & 3) < jmax) {
               const int px = idx >> 2, j = idx & 3;
-              const float x[8] = {__uint_as_float(va[u].x) * sx, __uint_as_float(va[u].y) * sx, __uint_as_float(va[u].z) * sx,
-                                  __uint_as_float(va[u].w) * sx, __uint_as_float(vb[u].x) * sx, __uint_as_float(vb[u].y) * sx,
-                                  __uint_as_float(vb[u].z) * sx, __uint_as_float(vb[u].w) * sx};
+              const uint32_t xin[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
               uint32_t h1[4], h2[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __half2 h = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
-                const float2 hf = __half22float2(h);
-                const __half2 l = __floats2half2_rn((x[2 * i] - hf.x) * 2048.f, (x[2 * i + 1] - hf.y) * 2048.f);
-                h1[i] = *reinterpret_cast<const uint32_t*>(&h);
-                h2[i] = *reinterpret_cast<const uint32_t*>(&l);
-              }
+              for (int i = 0; i < 4; ++i) split_f16_pair(xin[2 * i], xin[2 * i + 1], sx, h1[i], h2[i]);
               const uint32_t off = (uint32_t)px * 64u + (uint32_t)((j ^ ((px >> 1) & 3)) * 16);
               sts128(h1_p + off, make_uint4(h1[0], h1[1], h1[2], h1[3]));
               sts128(h2_p + off, make_uint4(h2[0], h2[1], h2[2], h2[3]));
             }
           }
         }
+        { PROF_BEGIN(s_fence);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
         mbar_arrive(a_ready + 8 * s);
+        PROF_END(s_fence); }
         PROF_END(s_split);
       }
-    if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); }
-  } else if (warp >= 8) {
+    if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); PROF_WRITE(11, s_bar); PROF_WRITE(12, s_fence); }
+  } else if (warp >= 8 && (!split8 || warp < 12)) {
     // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant.  More than 64
     // output channels: both groups work on every tile, group g on the 32-column chunks g and g+2.  Thin layers: group g owns
     // the CTA's tiles with local index & 1 == g, both chunks.  After every k-block the group adds that k-block's accumulators
@@ -711,9 +737,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     PROF_DECL(e_wait_full); PROF_DECL(e_drain); PROF_DECL(e_final);
     int ka = 0, it = 0;
     uint32_t ph_full0 = 0u, ph_full1 = 0u;                         // phase of this group's acc_full barrier of either set
-    const uint32_t my_full = acc_full + (thin ? 8u * (uint32_t)grp : 0u);
+    const uint32_t my_full = acc_full + (alt ? 8u * (uint32_t)grp : 0u);
+    uint32_t nstore = 0;
     for (int item = blockIdx.x; item < a.nitems; item += gridDim.x, ++it) {
-      if (thin && (it & 1) != grp) { ka += KB; continue; }          // the other group's tile
+      if (alt && (it & 1) != grp) { ka += KB; continue; }           // the other group's tile
       const int tile = item / a.nslices;
       const int n0 = (item - tile * a.nslices) * a.cout;
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
@@ -770,8 +797,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
           // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
           // store has finished READING it.
-          const uint32_t sbuf = sOut + (uint32_t)grp * OUT_SLOT;
-          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          // one staging tile per group; a single group (split8) alternates between both and only waits for the store before
+          // the previous one to have read its tile
+          const uint32_t sbuf = sOut + (split8 ? (nstore & 1u) : (uint32_t)grp) * OUT_SLOT;
+          ++nstore;
+          if (et == 0) {
+            if (split8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll
@@ -1022,6 +1055,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   TcArgs a;
   a.prof = g_conv_prof;
   a.pdl = pdl == 0 ? 0 : (pdl & 2 ? 2 : 1);
+  a.thin_mode = ((force >> 11) & 1) ? 2 : 1;           // force bit 11 (tuning): one epilogue group + eight splitter warps
   a.bias = bias; a.y = y; a.h = oh; a.w = ow; a.cout = cout; a.cout_real = cout_real; a.tma_out = tma_out ? 1 : 0;
   a.ys = y_pix_stride; a.kblocks = kb; a.alpha = leaky_alpha; a.w_scale = w_scale;
   a.s2d_c = stride == 1 ? 0 : cin;

@@ -97,6 +97,7 @@ class _Conv2D:
         self.tc_min_cin = 16        # thinner inputs (the RGB conv) stay on the FFMA2 kernel
         self.events = None          # optional list: receives (start, end) CUDA events around the launch (bench.py roofline)
         self.bias = None            # [cout]
+        self.host = None            # (kernel, bias) on the host, made on demand (first encoder layer, weights as kernel parameters)
         self._out = {}
         self._calls = 0             # tensor-core launches since the weights were (re)packed
 
@@ -107,6 +108,7 @@ class _Conv2D:
         self.kernel = k
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         self._calls = 0
+        self.host = None
         # tensor-core path (stride 1, or stride 2 with cin % 16 == 0; cout <= 256): TF32 hi/lo planes packed once per layer
         self.packed = None
         n = L.lib.m4d_conv3x3_tc_packed_floats_p(k.shape[2], self.filters, self.strides, self.prec)
@@ -218,7 +220,11 @@ class FeaturePyramid:
         # conv -> DN as two ops (default) or m4d_rgb_conv_dn, which never stores the conv output but evaluates it twice.
         # Measured on B200 (config 3): the fused call is 0.18 ms per step SLOWER - the 3->16 conv is instruction-bound
         # (~400 instructions per pixel), not bound by the 252 MB it writes, so recomputing it costs more than the traffic saved.
-        self.unfused_first_layer = os.environ.get("M4D_FUSED_FIRST_LAYER", "0") != "1"
+        # M4D_FUSED_FIRST_LAYER: 2 (default) = fused with the conv weights in the kernel parameter block (m4d_rgb_conv_dn_hostw:
+        # the conv becomes cheap enough that recomputing it beats the 252 MB round trips), 1 = fused, weights in shared memory,
+        # 0 = conv, then DN, as two ops.
+        self.first_layer_mode = int(os.environ.get("M4D_FUSED_FIRST_LAYER", "2"))
+        self.unfused_first_layer = self.first_layer_mode == 0
 
     def _first_layer_fused(self, conv1, images):
         dn = self.dn_layers[0]
@@ -233,6 +239,14 @@ class FeaturePyramid:
             ws = dn._ws[key] = (torch.empty(2 * b * 16, dtype=torch.float64, device=images.device),
                                 torch.empty((b, h, w, 16), dtype=torch.float32, device=images.device))
         stats, out = ws
+        if self.first_layer_mode == 2:
+            # weights in the kernel parameter block (constant operands of the FMAs): host copies, made once per assignment
+            if conv1.host is None:
+                conv1.host = (conv1.kernel.detach().cpu().contiguous(), conv1.bias.detach().cpu().contiguous())
+            hk, hb = conv1.host
+            L.check(L.lib.m4d_rgb_conv_dn_hostw(L.ptr(images), _pix_stride(images), hk.data_ptr(), hb.data_ptr(), b, h, w,
+                                                L.ptr(dn.scale), L.ptr(dn.bias), float(LEAKY), L.ptr(stats), L.ptr(out), L.stream()))
+            return out
         L.check(L.lib.m4d_rgb_conv_dn(L.ptr(images), _pix_stride(images), L.ptr(conv1.kernel), L.ptr(conv1.bias), b, h, w,
                                       L.ptr(dn.scale), L.ptr(dn.bias), float(LEAKY), L.ptr(stats), L.ptr(out), L.stream()))
         return out

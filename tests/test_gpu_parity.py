@@ -954,9 +954,10 @@ def test_first_encoder_layer_fused_conv_dn(shape):
     want = oracle.leaky_relu(dn(conv))
     settings = {"nbre_lvls": 1, "is_training": False, "ablation": m.M4depthAblationParameters()}
     outs = []
-    for unfused in (False, True):
+    for mode in (2, 0, 1):              # weights as kernel parameters (default) | two ops | fused, weights in shared memory
+        unfused = mode == 0
         enc = m.FeaturePyramid(settings)
-        enc.unfused_first_layer = unfused
+        enc.unfused_first_layer, enc.first_layer_mode = unfused, mode
         enc.conv_layers_s1[0].assign(wts["encoder/conv_layers_s1/0/kernel"], wts["encoder/conv_layers_s1/0/bias"], "cuda")
         enc.conv_layers_s2[0].assign(wts["encoder/conv_layers_s2/0/kernel"], wts["encoder/conv_layers_s2/0/bias"], "cuda")
         enc.dn_layers[0].scale = wts["encoder/dn_layers/0/scale"].cuda().reshape(1, 1, 1, -1).contiguous()
@@ -967,6 +968,8 @@ def test_first_encoder_layer_fused_conv_dn(shape):
         outs.append(tmp.clone())
     np.testing.assert_allclose(outs[0].cpu().numpy(), want.numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    # same FMA chain; the double-precision statistics are summed in another order (a last-bit difference of a mean at most)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[2].cpu().numpy(), rtol=2e-6, atol=1e-6)
 
 
 def test_test_step_protocol_single_frames_and_kitti_sequence_mode():
