@@ -172,6 +172,13 @@ int m4d_rgb_conv_dn(const float* x, int x_pix_stride, const float* kernel_hwio, 
 /* The same call with the conv kernel [3,3,3,16] and its bias given as HOST pointers: they travel in the kernel parameter block
  * and are read as constant operands of the FMAs (no shared-memory weight loads: ~2x faster than the call above, and faster
  * than storing the conv output).  Same results bit for bit.  Everything else as above (x, DN parameters, workspace: device). */
+/* The two halves of the first encoder layer as separate calls: the conv (weights as HOST pointers, as below) evaluated once,
+ * y = conv3x3_same(x) + bias stored [b,h,w,16] and its per-(image, channel) sum / sum of squares accumulated into stats_ws
+ * (2*b*16 doubles, zeroed by the call); then the apply pass of DomainNormalization on those statistics (c = 16 or 32). */
+int m4d_rgb_conv_stats_hostw(const float* x, int x_pix_stride, const float* kernel_hwio_host, const float* conv_bias_host, int b,
+                             int h, int w, float* y, double* stats_ws, void* stream);
+int m4d_domain_norm_apply(const float* x, int b, int h, int w, int c, const float* scale, const float* bias, float leaky_alpha,
+                          const double* stats_ws, float* out, void* stream);
 int m4d_rgb_conv_dn_hostw(const float* x, int x_pix_stride, const float* kernel_hwio_host, const float* conv_bias_host, int b, int h,
                           int w, const float* dn_scale, const float* dn_bias, float leaky_alpha, double* stats_ws, float* out,
                           void* stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "m4d_domain_norm": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p]),
     "m4d_rgb_conv_dn": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _f, _p, _p, _p]),
     "m4d_rgb_conv_dn_hostw": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _f, _p, _p, _p]),
+    "m4d_rgb_conv_stats_hostw": (_i, [_p, _i, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "m4d_domain_norm_apply": (_i, [_p, _i, _i, _i, _i, _p, _p, _f, _p, _p, _p]),
     "m4d_conv3x3_nhwc": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _i, _p]),
     "m4d_conv3x3_tc_packed_floats": (C.c_int64, [_i, _i]),
     "m4d_conv3x3_tc_pack": (_i, [_p, _i, _i, _p, _p]),

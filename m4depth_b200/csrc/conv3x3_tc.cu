@@ -734,7 +734,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int et = threadIdx.x - 256 - grp * 128;                  // 0..127 within the group
     // staging tiles for the TMA stores: one per group
     const int nchunks = (a.cout + 31) >> 5;
-    PROF_DECL(e_wait_full); PROF_DECL(e_drain); PROF_DECL(e_final);
+    PROF_DECL(e_wait_full); PROF_DECL(e_drain); PROF_DECL(e_final); PROF_DECL(e_store_wait);
     int ka = 0, it = 0;
     uint32_t ph_full0 = 0u, ph_full1 = 0u;                         // phase of this group's acc_full barrier of either set
     const uint32_t my_full = acc_full + (alt ? 8u * (uint32_t)grp : 0u);
@@ -801,11 +801,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           // the previous one to have read its tile
           const uint32_t sbuf = sOut + (split8 ? (nstore & 1u) : (uint32_t)grp) * OUT_SLOT;
           ++nstore;
+          { PROF_BEGIN(e_store_wait);
           if (et == 0) {
             if (split8) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+          PROF_END(e_store_wait); }
           const uint32_t rowp = sbuf + (uint32_t)m * 128u;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -830,7 +832,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       PROF_END(e_final);
     }
     if (a.tma_out && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store's reads
-    if (warp == 8) { PROF_WRITE(7, e_wait_full); PROF_WRITE(8, e_drain); PROF_WRITE(9, e_final); }
+    if (warp == 8) { PROF_WRITE(7, e_wait_full); PROF_WRITE(8, e_drain); PROF_WRITE(9, e_final); PROF_WRITE(13, e_store_wait); }
   }
 
   tc_fence_before();

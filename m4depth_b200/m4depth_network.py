@@ -220,10 +220,12 @@ class FeaturePyramid:
         # conv -> DN as two ops (default) or m4d_rgb_conv_dn, which never stores the conv output but evaluates it twice.
         # Measured on B200 (config 3): the fused call is 0.18 ms per step SLOWER - the 3->16 conv is instruction-bound
         # (~400 instructions per pixel), not bound by the 252 MB it writes, so recomputing it costs more than the traffic saved.
-        # M4D_FUSED_FIRST_LAYER: 2 (default) = fused with the conv weights in the kernel parameter block (m4d_rgb_conv_dn_hostw:
-        # the conv becomes cheap enough that recomputing it beats the 252 MB round trips), 1 = fused, weights in shared memory,
-        # 0 = conv, then DN, as two ops.
-        self.first_layer_mode = int(os.environ.get("M4D_FUSED_FIRST_LAYER", "2"))
+        # M4D_FUSED_FIRST_LAYER: 3 (default) = the conv evaluated once with its weights in the kernel parameter block, output stored
+        # and DN statistics accumulated on the way, then DN's apply pass (m4d_rgb_conv_stats_hostw + m4d_domain_norm_apply);
+        # 2 = conv recomputed in both DN passes, weights as parameters (m4d_rgb_conv_dn_hostw); 1 = the same with the weights in
+        # shared memory; 0 = conv (shared-memory weights), DN statistics, DN apply as three kernels.
+        # Measured on B200 (config 3, frames/s, same box): 3: 1467-1471, 2: 1435-1452, 0: 1439-1451.
+        self.first_layer_mode = int(os.environ.get("M4D_FUSED_FIRST_LAYER", "3"))
         self.unfused_first_layer = self.first_layer_mode == 0
 
     def _first_layer_fused(self, conv1, images):
@@ -239,6 +241,19 @@ class FeaturePyramid:
             ws = dn._ws[key] = (torch.empty(2 * b * 16, dtype=torch.float64, device=images.device),
                                 torch.empty((b, h, w, 16), dtype=torch.float32, device=images.device))
         stats, out = ws
+        if self.first_layer_mode == 3:
+            # conv evaluated once (weights as kernel parameters), stored, statistics accumulated on the way; then DN's apply pass
+            if conv1.host is None:
+                conv1.host = (conv1.kernel.detach().cpu().contiguous(), conv1.bias.detach().cpu().contiguous())
+            hk, hb = conv1.host
+            y = dn._ws.get(("y",) + key)
+            if y is None:
+                y = dn._ws[("y",) + key] = torch.empty((b, h, w, 16), dtype=torch.float32, device=images.device)
+            L.check(L.lib.m4d_rgb_conv_stats_hostw(L.ptr(images), _pix_stride(images), hk.data_ptr(), hb.data_ptr(), b, h, w,
+                                                   L.ptr(y), L.ptr(stats), L.stream()))
+            L.check(L.lib.m4d_domain_norm_apply(L.ptr(y), b, h, w, 16, L.ptr(dn.scale), L.ptr(dn.bias), float(LEAKY), L.ptr(stats),
+                                                L.ptr(out), L.stream()))
+            return out
         if self.first_layer_mode == 2:
             # weights in the kernel parameter block (constant operands of the FMAs): host copies, made once per assignment
             if conv1.host is None:

@@ -954,7 +954,7 @@ def test_first_encoder_layer_fused_conv_dn(shape):
     want = oracle.leaky_relu(dn(conv))
     settings = {"nbre_lvls": 1, "is_training": False, "ablation": m.M4depthAblationParameters()}
     outs = []
-    for mode in (2, 0, 1):              # weights as kernel parameters (default) | two ops | fused, weights in shared memory
+    for mode in (2, 0, 1, 3):           # weights as kernel parameters | two ops | fused, weights in shared memory | conv once + stats
         unfused = mode == 0
         enc = m.FeaturePyramid(settings)
         enc.unfused_first_layer, enc.first_layer_mode = unfused, mode
@@ -970,6 +970,7 @@ def test_first_encoder_layer_fused_conv_dn(shape):
     np.testing.assert_allclose(outs[0].cpu().numpy(), outs[1].cpu().numpy(), rtol=1e-5, atol=1e-6)
     # same FMA chain; the double-precision statistics are summed in another order (a last-bit difference of a mean at most)
     np.testing.assert_allclose(outs[0].cpu().numpy(), outs[2].cpu().numpy(), rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(outs[0].cpu().numpy(), outs[3].cpu().numpy(), rtol=1e-5, atol=1e-6)
 
 
 def test_test_step_protocol_single_frames_and_kitti_sequence_mode():
@@ -1047,6 +1048,10 @@ def test_resize_and_prologue_epilogue_vs_oracle():
     n = e(b, 2 * h, 2 * w, 1)
     L.check(L.lib.m4d_resize_nearest(d[3].data_ptr(), b, h, w, 1, 2 * h, 2 * w, n.data_ptr(), L.stream()))
     assert torch.equal(n.cpu(), oracle.resize_nearest(state, 2 * h, 2 * w))
+    for oh2, ow2 in ((3 * h + 1, 4 * ((5 * w) // 8)), (h + 3, 2 * w + 1)):      # non-integer factors: 16-byte-store kernel, generic kernel
+        n2 = e(b, oh2, ow2, 1)
+        L.check(L.lib.m4d_resize_nearest(d[3].data_ptr(), b, h, w, 1, oh2, ow2, n2.data_ptr(), L.stream()))
+        assert torch.equal(n2.cpu(), oracle.resize_nearest(state, oh2, ow2))
     # epilogue
     rr = torch.randn(b, h, w, 5, generator=g) * 3
     rr[0, 0, 0, 0] = 9.0       # clipped at 7
