@@ -311,6 +311,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t s_max = tmem_slot + 16;                                      // [MAX_A_STAGES (4 slots)] uint: max |x| bits of the landed halo
   const uint32_t s_scale = s_max + 16;                                        // [8] float: 1 / (s_x * s_w) of k-block ka & 7 (8 slots: the splitters run up to 3 k-blocks ahead of the MMAs, the epilogue one behind)
 
+  const uint32_t s_bias = sBar + 1024;                                        // [256] float: the layer's bias (zero beyond cout_real)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = a.kblocks, NB = a.nb, NA = a.na;
   // Programmatic dependent launch (a.pdl): the next kernel in the stream may be scheduled as soon as every CTA of this grid
@@ -330,6 +331,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t nsplit = split8 ? 256u : 128u;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
+  // The bias goes to shared memory once per CTA: the epilogue used to fetch its 32 values per chunk with __ldg for every tile,
+  // and with the whole L1 carved out as shared memory each fetch was an L2 round trip - ~3500 clocks per 32-channel chunk of
+  // every tile (role timers), which made the epilogue the pace-setter of every layer with one or two k-blocks per tile.
+  if (threadIdx.x < 256) {
+    if (a.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");      // bias possibly written by the preceding grid
+    const float bv = (int)threadIdx.x < a.cout_real ? __ldg(a.bias + threadIdx.x) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_bias + 4 * threadIdx.x), "f"(bv) : "memory");
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_A_STAGES; ++s) {
       mbar_init(a_full + 8 * s, 1);
@@ -792,7 +801,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         const int nc = a.cout - c0 >= 32 ? 32 : 16;
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (i < nc) sum[ci][i] = leaky(sum[ci][i] + (n0 + c0 + i < a.cout_real ? __ldg(a.bias + n0 + c0 + i) : 0.f), a.alpha);
+          if (i < nc) {
+            float bv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(bv) : "r"(s_bias + 4u * (uint32_t)(n0 + c0 + i)));
+            sum[ci][i] = leaky(sum[ci][i] + bv, a.alpha);
+          }
         if (a.tma_out) {
           // staging tile [128 px][32 ch] in the SWIZZLE_128B layout the store's tensor map expects: 16-byte chunk c of
           // row m lives at chunk c ^ (m & 7).  One buffer per group: the issuing thread first waits until the previous
@@ -1080,10 +1093,10 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   const size_t a_stage = half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
   const size_t stage = (size_t)2 * cout * (half ? 64 : 128);
   int na = force_na > 0 ? force_na : 2;                           // (a third stage measured no gain: the weight ring was the limit)
-  size_t fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024;
+  size_t fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024 + 1024;     // alignment, halo stages, staging tiles, barriers, bias
   if (na > 2 && (227 * 1024 < fixed + 4 * stage)) {
     na = 2;
-    fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024;
+    fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024 + 1024;
   }
   M4D_REQUIRE(na >= 2 && na <= MAX_A_STAGES && 227 * 1024 >= fixed + 2 * stage, "m4d_conv3x3_tc_fwd: not enough shared memory for the pipeline");
   int nb = (int)((227 * 1024 - fixed) / stage);
