@@ -84,6 +84,8 @@ INTERP_GATHER, INTERP_BP, INTERP_BP_FMA = 0, 1, 2
 INTERP_FLAG_GENERIC = 0x100     # OR into interp: shape-generic PSCV kernel instead of the specialised one
 INTERP_FLAG_TILE = 0x200        # OR into interp: CTA-tile K=9 kernel instead of the warp-autonomous one
 INTERP_FLAG_WARP = 0x400        # OR into interp: warp-autonomous LDG-gather kernel instead of the shared-memory staged one
+INTERP_VARIANT_STAGED_8 = 0x1000      # OR into interp (tuning / tests): staged kernel, 16x8 tiles, phases in sequence (pscv9s_kernel)
+INTERP_VARIANT_STAGED_4 = 0x2000      # staged kernel, 16x4 tiles
 
 
 class M4DError(RuntimeError):

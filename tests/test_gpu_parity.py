@@ -417,7 +417,8 @@ def test_pscv_smem_staged_kernel_equals_ldg_kernels(shape, data):
         pl[torch.rand(b, h, w, 1, generator=g) < 0.05] = float("nan")
     args = [cu(x) for x in (c1, c2, pt, pl, rot, trans)]
     dc = dev_cam(cam)
-    flags = (0, L.INTERP_FLAG_WARP) + ((L.INTERP_FLAG_GENERIC,) if b * h * w <= 20000 else ())
+    flags = (0, L.INTERP_VARIANT_STAGED_8, L.INTERP_VARIANT_STAGED_4, L.INTERP_FLAG_WARP) + (
+        (L.INTERP_FLAG_GENERIC,) if b * h * w <= 20000 else ())
     res = []
     for flag in flags:
         cv, pd, idx = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=flag, return_index_grids=True)
