@@ -86,6 +86,7 @@ INTERP_FLAG_TILE = 0x200        # OR into interp: CTA-tile K=9 kernel instead of
 INTERP_FLAG_WARP = 0x400        # OR into interp: warp-autonomous LDG-gather kernel instead of the shared-memory staged one
 INTERP_VARIANT_STAGED_8 = 0x1000      # OR into interp (tuning / tests): staged kernel, 16x8 tiles, phases in sequence (pscv9s_kernel)
 INTERP_VARIANT_STAGED_4 = 0x2000      # staged kernel, 16x4 tiles
+INTERP_VARIANT_STAGED_C16 = 0x4000    # c = 16, one group (level 1): the staged kernel with 32x8 tiles and 64-byte pixel rows
 
 
 class M4DError(RuntimeError):

@@ -437,6 +437,48 @@ def test_pscv_smem_staged_kernel_equals_ldg_kernels(shape, data):
     assert torch.equal(bits(wide[..., :18]), bits(cv)) and torch.all(wide[..., 18:121] == -7.0) and torch.all(wide[..., 122:] == -7.0)
 
 
+@pytest.mark.parametrize("shape", [(8, 192, 640), (2, 96, 96), (3, 37, 53), (1, 120, 160), (2, 9, 17), (1, 2, 2)])
+@pytest.mark.parametrize("data", ["micro", "insitu", "far", "nan"])
+def test_pscv_smem_staged_kernel_level1_shape_equals_ldg_kernels(shape, data):
+    """The staged kernel instantiated for level 1 (c = 16, one group: 32x8-pixel tiles, 64-byte pixel rows, quad rotation by pixel
+    pairs) against the warp-autonomous LDG kernel that level runs by default and, at small sizes, the shape-generic one: cv,
+    prev_disp, integer tap grids and the fused log(centre) output bit for bit, on the same four parallax distributions."""
+    m = _m4d()
+    L = m._lib
+    b, h, w = shape
+    c, cuts = 16, 1
+    c1, c2, pt, pl, rot, trans, cam = pscv_inputs(700 + h + w, b, h, w, c, cuts, "kitti")
+    g = torch.Generator().manual_seed(h * w + 1)
+    if data == "insitu":
+        pl = 0.6 + 1.7 * torch.rand(b, h, w, 1, generator=g)
+    elif data == "far":
+        pl = pl * torch.where(torch.rand(b, h, w, 1, generator=g) < 0.02, 30.0, 1.0)
+        pl[:, : max(1, h // 4)] *= -1.0
+    elif data == "nan":
+        pl[0, : min(h, 17)] = float("nan")
+        pl[-1, -1, -1] = float("inf")
+        pl[torch.rand(b, h, w, 1, generator=g) < 0.05] = float("nan")
+    args = [cu(x) for x in (c1, c2, pt, pl, rot, trans)]
+    dc = dev_cam(cam)
+    flags = (L.INTERP_VARIANT_STAGED_C16, 0) + ((L.INTERP_FLAG_GENERIC,) if b * h * w <= 20000 else ())
+    res = []
+    for flag in flags:
+        cv, pd, idx = m.utils.get_parallax_sweeping_cv(*args, dc, 4, nbre_cuts=cuts, interp=flag, return_index_grids=True)
+        xs = 64
+        wide = torch.full((b, h, w, xs), -7.0, device="cuda")
+        L.check(L.lib.m4d_pscv_fused_fwd_ex(
+            L.ptr(args[0]), L.ptr(args[1]), L.ptr(args[2]), L.ptr(args[3]), L.ptr(args[4]), 4, L.ptr(args[5]), L.ptr(dc["f"]),
+            L.ptr(dc["c"]), b, h, w, c, cuts, 4, wide.data_ptr(), xs, None, 0, wide.data_ptr() + 4 * 63, xs, 2.0,
+            None, flag, L.stream()))
+        res.append((cv.cpu(), pd.cpu(), idx.cpu(), wide.cpu()))
+    bits = lambda t: t.view(torch.int32) if t.dtype == torch.float32 else t
+    for other in res[1:]:
+        for a_, b_ in zip(res[0], other):
+            assert torch.equal(bits(a_), bits(b_))
+    cv, _, _, wide = res[0]
+    assert torch.equal(bits(wide[..., :9]), bits(cv)) and torch.all(wide[..., 9:63] == -7.0)
+
+
 @pytest.mark.parametrize("interp", ["gather", "bp"])
 def test_pscv_degenerate_inputs(interp):
     """What the reference's arithmetic does with degenerate inputs must come out the same: zero translation (s = 0: 0/0 in the
