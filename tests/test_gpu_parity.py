@@ -1115,6 +1115,18 @@ def test_group_l2norm_and_dn_vs_oracle():
     out = torch.empty_like(x, device="cuda")
     L.check(L.lib.m4d_group_l2norm(cu(x).data_ptr(), 2 * 9 * 11, 96, 4, out.data_ptr(), L.stream()))
     np.testing.assert_allclose(out.cpu().numpy(), oracle.group_l2_normalize(x, 4).numpy(), rtol=5e-7, atol=0)
+    # every (channels, groups) pair of the network (m4depth_network.py:172-189): 16- and 32-channel groups run the
+    # warp-cooperative kernel, 24-channel groups the one-thread-per-group kernel; in place as well; a zero group gives NaN (no epsilon)
+    for c, cuts in ((16, 1), (32, 2), (64, 2), (96, 4), (128, 4), (192, 8)):
+        x = torch.randn(3, 7, 13, c, generator=g) * 3.0
+        x[1, 2, 3, : c // cuts] = 0.0
+        want = oracle.group_l2_normalize(x, cuts)
+        buf = cu(x).clone()
+        L.check(L.lib.m4d_group_l2norm(buf.data_ptr(), 3 * 7 * 13, c, cuts, buf.data_ptr(), L.stream()))
+        got = buf.cpu()
+        assert torch.equal(torch.isnan(got), torch.isnan(want))
+        ok = ~torch.isnan(want)
+        np.testing.assert_allclose(got[ok].numpy(), want[ok].numpy(), rtol=5e-7, atol=0)
     # DN at an encoder-like shape, random affine, fused leaky
     xx = torch.randn(2, 48, 64, 16, generator=g) * (torch.rand(1, 1, 1, 16, generator=g) * 2 + 0.1) + torch.randn(1, 1, 1, 16, generator=g)
     sc, bi = torch.rand(1, 1, 1, 16, generator=g) + 0.5, torch.randn(1, 1, 1, 16, generator=g) * 0.1
