@@ -1087,22 +1087,6 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.concat = (cout <= 64 || !((force >> 10) & 1)) ? 1 : 0;
   a.nacc = 2;
   a.nsets = 2;
-  // halo stages: a k-block's chain TMA load -> split -> MMAs -> release is several thousand clocks of latency; with few
-  // output channels the MMAs are short and two stages leave the tensor pipe waiting, so take a third where the weight
-  // ring still gets >= 4 stages
-  const size_t a_stage = half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
-  const size_t stage = (size_t)2 * cout * (half ? 64 : 128);
-  int na = force_na > 0 ? force_na : 2;                           // (a third stage measured no gain: the weight ring was the limit)
-  size_t fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024 + 1024;     // alignment, halo stages, staging tiles, barriers, bias
-  if (na > 2 && (227 * 1024 < fixed + 4 * stage)) {
-    na = 2;
-    fixed = 1024 + (size_t)na * a_stage + 2 * OUT_SLOT + 1024 + 1024;
-  }
-  M4D_REQUIRE(na >= 2 && na <= MAX_A_STAGES && 227 * 1024 >= fixed + 2 * stage, "m4d_conv3x3_tc_fwd: not enough shared memory for the pipeline");
-  int nb = (int)((227 * 1024 - fixed) / stage);
-  if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
-  a.nb = nb;
-  a.na = na;
   // weight slabs a tile streams through the ring: (k-block, tap) pairs that carry weights
   int slabs = 0;
   for (int k = 0; k < kb; ++k) {
@@ -1110,6 +1094,25 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     const int chunks = 2 * cin / KC, py = k / chunks, left = cin - (k - py * chunks) * KC;
     slabs += (py ? 1 : 2) * (left > 0 ? 2 : 1);
   }
+  // halo stages: a k-block's chain TMA load -> split -> MMAs -> release is several thousand clocks of latency.  Two stages by
+  // default; a third for the thinnest layers (Cout <= 32) where the whole layer's weights still stay resident beside it: measured
+  // 16->16 stride 2 @384x1280 155 -> 142 us, 32->32 stride 2 85 -> 78, 16->32 95 -> 89, 32->16 97 -> 93 (wider layers lose their
+  // resident weights to the third stage and get slower: 64->32 183 -> 195 us)
+  const size_t a_stage = half ? A_STAGE_BYTES_F16 : A_STAGE_BYTES_F32;
+  const size_t stage = (size_t)2 * cout * (half ? 64 : 128);
+  auto fixed_for = [&](int n) { return (size_t)1024 + (size_t)n * a_stage + 2 * OUT_SLOT + 1024 + 1024; };   // alignment, halo stages, staging tiles, barriers, bias
+  int na = force_na > 0 ? force_na : 2;
+  if (force_na == 0 && cout <= 32 && nslices == 1 && MAX_A_STAGES >= 3 && 227 * 1024 >= fixed_for(3) + (size_t)slabs * stage) na = 3;
+  size_t fixed = fixed_for(na);
+  if (na > 2 && (227 * 1024 < fixed + 4 * stage)) {
+    na = 2;
+    fixed = fixed_for(na);
+  }
+  M4D_REQUIRE(na >= 2 && na <= MAX_A_STAGES && 227 * 1024 >= fixed + 2 * stage, "m4d_conv3x3_tc_fwd: not enough shared memory for the pipeline");
+  int nb = (int)((227 * 1024 - fixed) / stage);
+  if (nb > MAX_B_STAGES) nb = MAX_B_STAGES;
+  a.nb = nb;
+  a.na = na;
   // Thin layers issue a tap's MMAs in ~100-200 clocks, far less than the latency of the TMA load that refills its stage, so
   // the ring is deep (up to 32 slabs) and, where the whole layer fits, loaded once per CTA instead of once per tile.
   a.b_resident = (nslices == 1 && slabs <= nb) ? 1 : 0;
