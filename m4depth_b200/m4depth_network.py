@@ -108,7 +108,9 @@ class _Conv2D:
         self.kernel = k
         self.bias = bias.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
         self._calls = 0
-        self.host = None
+        # the first encoder layer's fused kernels take their 3x3x3x16 weights as kernel parameters: host copies made here, not
+        # lazily inside a call (a device-to-host copy is not allowed while a CUDA graph is being captured)
+        self.host = (k.detach().cpu().contiguous(), self.bias.detach().cpu().contiguous()) if k.shape[2] == 3 and self.filters == 16 else None
         # tensor-core path (stride 1, or stride 2 with cin % 16 == 0; cout <= 256): TF32 hi/lo planes packed once per layer
         self.packed = None
         n = L.lib.m4d_conv3x3_tc_packed_floats_p(k.shape[2], self.filters, self.strides, self.prec)
