@@ -690,8 +690,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
           // largest magnitude of the k-block's halo (from here on as the bits of |x|: monotonic for non-negative floats)
           uint32_t mx = __float_as_uint(mxf);
-#pragma unroll
-          for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+          mx = __reduce_max_sync(0xFFFFFFFFu, mx);           // one REDUX instead of five dependent shuffles
           // four slots in rotation: slot (ka & 3) collects this k-block's maximum, slot (ka + 2) & 3 - read two k-blocks ago, not
           // needed before two k-blocks from now - is cleared, so one barrier per k-block suffices
           const uint32_t slot = s_max + 4 * (uint32_t)(ka & 3);
