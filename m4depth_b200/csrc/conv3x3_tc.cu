@@ -639,7 +639,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
     const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
     const int NS = (int)nsplit;
-    PROF_DECL(s_wait_full); PROF_DECL(s_split); PROF_DECL(s_bar); PROF_DECL(s_fence);
+    PROF_DECL(s_wait_full); PROF_DECL(s_split); PROF_DECL(s_bar); PROF_DECL(s_fence); PROF_DECL(s_load); PROF_DECL(s_cvt);
     // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
     if (a.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     const float w_inv_scale = HALF ? __ldg(a.w_scale) : 1.f;
@@ -690,6 +690,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
           // largest magnitude of the k-block's halo (from here on as the bits of |x|: monotonic for non-negative floats)
           uint32_t mx = __float_as_uint(mxf);
+#ifdef M4D_TC_PROFILE
+          prof_s_load += clock64() - prof_t0_s_split;          // loads + per-thread maximum
+#endif
           mx = __reduce_max_sync(0xFFFFFFFFu, mx);           // one REDUX instead of five dependent shuffles
           // four slots in rotation: slot (ka & 3) collects this k-block's maximum, slot (ka + 2) & 3 - read two k-blocks ago, not
           // needed before two k-blocks from now - is cleared, so one barrier per k-block suffices
@@ -709,6 +712,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_scale + 4 * (ka & 7)), "f"(inv) : "memory");
           }
           const uint32_t h1_p = hi_p + A_SLOT, h2_p = h1_p + AH_PLANE;
+          PROF_BEGIN(s_cvt);
 #pragma unroll
           for (int u = 0; u < UPT; ++u) {
             const int idx = t + u * NS;
@@ -723,6 +727,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               sts128(h2_p + off, make_uint4(h2[0], h2[1], h2[2], h2[3]));
             }
           }
+          PROF_END(s_cvt);
         }
         { PROF_BEGIN(s_fence);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
@@ -730,7 +735,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         PROF_END(s_fence); }
         PROF_END(s_split);
       }
-    if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); PROF_WRITE(11, s_bar); PROF_WRITE(12, s_fence); }
+    if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); PROF_WRITE(11, s_bar); PROF_WRITE(12, s_fence); PROF_WRITE(14, s_load); PROF_WRITE(15, s_cvt); }
   } else if (warp >= 8 && (!split8 || warp < 12)) {
     // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant.  More than 64
     // output channels: both groups work on every tile, group g on the 32-column chunks g and g+2.  Thin layers: group g owns

@@ -16,7 +16,7 @@ from m4depth_b200.m4depth_network import _Conv2D
 
 L = m._lib
 NAMES = ["A:wait_empty", "I:wait_acc", "I:wait_halo", "I:wait_wgt", "I:issue", "S:wait_landed", "S:split", "E:wait_acc", "E:drain", "E:final",
-         "CTA:life", "S:bar", "S:fence", "E:store_wait"]          # E:* are group 0's (thin layers: it owns every other tile); CTA:life = SM clocks the CTA ran for
+         "CTA:life", "S:bar", "S:fence", "E:store_wait", "S:load+max", "S:convert"]          # E:* are group 0's (thin layers: it owns every other tile); CTA:life = SM clocks the CTA ran for
 
 
 def run(b, h, w, cin, cout, stride):
