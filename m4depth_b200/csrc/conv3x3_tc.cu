@@ -290,8 +290,11 @@ __device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& l
 // per (pixel tile, k-block) for the activations (by the splitter warps, from the landed halo) - so fp16's narrow exponent
 // range costs nothing: the epilogue warps multiply each k-block's accumulators by 1 / (s_x * s_w) (and the cross terms by
 // 2^-11) while adding them into their fp32 register sums.  fp16 x fp16 products are exact in the fp32 accumulator.
-template <bool S2D, bool CONCAT, bool HALF>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// WS ("wide split", layers with at most 32 output channels): 20 warps - warps 16-19 are four more splitter warps (the split
+// is the longest role of those layers) while both epilogue groups keep alternating tiles; the register budget of 640 threads
+// (96 per thread) holds because such a layer's epilogue owns a single 32-column chunk.
+template <bool S2D, bool CONCAT, bool HALF, bool WS = false>
+__global__ void __launch_bounds__(WS ? NTHREADS + 128 : NTHREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_y, TcArgs a) {
   extern __shared__ unsigned char smem_raw[];
@@ -326,9 +329,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   // a tile's accumulators to the acc_full barrier of the group that owns the tile.
   // (thin_mode 2, tuning: one epilogue group for every tile and warps 12-15 as four more splitter warps)
   const bool thin = a.cout <= 64;
-  const bool alt = thin && a.thin_mode != 2;                       // epilogue groups alternate tiles
-  const bool split8 = thin && a.thin_mode == 2;
-  const uint32_t nsplit = split8 ? 256u : 128u;
+  const bool split8 = !WS && thin && a.thin_mode == 2;             // (tuning) one epilogue group, warps 12-15 split
+  const bool alt = thin && !split8;                                // epilogue groups alternate tiles
+  const uint32_t nsplit = (WS || split8) ? 256u : 128u;
   const int tiles_per_img = a.tiles_x * a.tiles_y;
 
   // The bias goes to shared memory once per CTA: the epilogue used to fetch its 32 values per chunk with __ldg for every tile,
@@ -635,9 +638,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     PROF_WRITE(1, i_wait_acc); PROF_WRITE(2, i_wait_a); PROF_WRITE(3, i_wait_b); PROF_WRITE(4, i_issue);
-  } else if ((warp >= 4 && warp < 8) || (split8 && warp >= 12)) {
+  } else if ((warp >= 4 && warp < 8) || (WS ? warp >= 16 : (split8 && warp >= 12))) {
     // ===== splitter: fp32 halo -> tf32 hi (in place) + lo plane, element-wise on the swizzled bytes / -> scaled fp16 planes
-    const int t = warp < 8 ? threadIdx.x - 128 : threadIdx.x - 384 + 128;
+    const int t = warp < 8 ? threadIdx.x - 128 : (WS ? threadIdx.x - 512 + 128 : threadIdx.x - 384 + 128);
     const int NS = (int)nsplit;
     PROF_DECL(s_wait_full); PROF_DECL(s_split); PROF_DECL(s_bar); PROF_DECL(s_fence); PROF_DECL(s_load); PROF_DECL(s_cvt);
     // (read once: a global load per k-block in thread 0's path delayed the whole split by its latency)
@@ -736,7 +739,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         PROF_END(s_split);
       }
     if (warp == 4) { PROF_WRITE(5, s_wait_full); PROF_WRITE(6, s_split); PROF_WRITE(11, s_bar); PROF_WRITE(12, s_fence); PROF_WRITE(14, s_load); PROF_WRITE(15, s_cvt); }
-  } else if (warp >= 8 && (!split8 || warp < 12)) {
+  } else if (warp >= 8 && warp < 16 && (!split8 || warp < 12)) {
     // ===== epilogue: two groups of four warps; a warp owns the accumulator rows (pixels) of its TMEM lane quadrant.  More than 64
     // output channels: both groups work on every tile, group g on the 32-column chunks g and g+2.  Thin layers: group g owns
     // the CTA's tiles with local index & 1 == g, both chunks.  After every k-block the group adds that k-block's accumulators
@@ -758,7 +761,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int n0 = (item - tile * a.nslices) * a.cout;
       const int bi = tile / tiles_per_img, r = tile - bi * tiles_per_img;
       const int oy0 = (r / a.tiles_x) * TILE_H, ox0 = (r % a.tiles_x) * TILE_W;
-      float sum[2][32];
+      constexpr int NCI = WS ? 1 : 2;                                // 32-column chunks an epilogue thread owns
+      float sum[NCI][32];
       for (int kb = 0; kb < KB; ++kb, ++ka) {
         const int set = ka & 1;
         { PROF_BEGIN(e_wait_full); mbar_wait(my_full + 16 * set, set ? ph_full1 : ph_full0); PROF_END(e_wait_full); }
@@ -770,7 +774,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (HALF) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(inv_main) : "r"(s_scale + 4 * (ka & 7)) : "memory");
         const float inv_cross = inv_main * (1.0f / 2048.0f);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
+        for (int ci = 0; ci < NCI; ++ci) {
           const int c0 = (thin ? ci : grp + 2 * ci) * 32;
           if (c0 < a.cout) {
             const int nc = a.cout - c0 >= 32 ? 32 : 16;
@@ -799,7 +803,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const bool valid = oy < a.h && ox < a.w;
       float* yp = a.y + (((size_t)bi * a.h + (valid ? oy : 0)) * a.w + (valid ? ox : 0)) * a.ys;
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
+      for (int ci = 0; ci < NCI; ++ci) {
         const int c0 = (thin ? ci : grp + 2 * ci) * 32;
         if ((thin ? ci : grp + 2 * ci) >= nchunks) continue;
         const int nc = a.cout - c0 >= 32 ? 32 : 16;
@@ -1122,6 +1126,9 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   a.b_resident = (nslices == 1 && slabs <= nb) ? 1 : 0;
   const size_t smem = fixed + (size_t)nb * stage;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, TcArgs);
+  // at most 32 output channels per work item (3xFP16): the 20-warp variant with eight splitter warps (force bit 12: off)
+  const bool ws = half && a.concat && cout <= 32 && !((force >> 12) & 1) && a.thin_mode != 2;
+  static const KernelFn kernels_ws[2] = {conv3x3_tc_kernel<false, true, true, true>, conv3x3_tc_kernel<true, true, true, true>};
   static const KernelFn kernels[8] = {conv3x3_tc_kernel<false, false, false>, conv3x3_tc_kernel<false, true, false>,
                                       conv3x3_tc_kernel<true, false, false>,  conv3x3_tc_kernel<true, true, false>,
                                       conv3x3_tc_kernel<false, false, true>,  conv3x3_tc_kernel<false, true, true>,
@@ -1133,8 +1140,8 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
   cudaGetDevice(&dev_id);
   std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
   if (!attr_set.load(std::memory_order_acquire)) {
-    for (int i = 0; i < 8; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int i = 0; i < 10; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(i < 8 ? kernels[i] : kernels_ws[i - 8], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) {
         m4d_set_error("m4d_conv3x3_tc_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
         return M4D_ECUDA;
@@ -1143,11 +1150,12 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
     attr_set.store(true, std::memory_order_release);
   }
   const int grid = a.nitems < m4d_sm_count() ? a.nitems : m4d_sm_count();
-  KernelFn kern = kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)];
+  KernelFn kern = ws ? kernels_ws[stride == 2 ? 1 : 0] : kernels[(half ? 4 : 0) + (stride == 2 ? 2 : 0) + (a.concat ? 1 : 0)];
+  const int nthreads = ws ? NTHREADS + 128 : NTHREADS;
   if (a.pdl) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(NTHREADS);
+    cfg.blockDim = dim3(nthreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -1161,7 +1169,7 @@ int tc_launch(const float* x, int x_pix_stride, const float* packed, const float
       return M4D_ECUDA;
     }
   } else {
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw, my, a);
+    kern<<<grid, nthreads, smem, stream>>>(mx, mw, my, a);
   }
   M4D_CHECK_LAUNCH("m4d_conv3x3_tc_fwd");
   return M4D_OK;
