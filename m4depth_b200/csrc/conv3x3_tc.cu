@@ -624,7 +624,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                   tc_mma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
                 }
               }
-              tc_commit(b_empty + 8 * sbs[j]);                      // (nobody waits for it when the weights are resident)
+              if (!a.b_resident) tc_commit(b_empty + 8 * sbs[j]);   // resident slabs are never released (and an arrival nobody
+                                                                    // waits for is what synccheck reports as a missing wait)
             }
             if (ky == tp.ky_hi) {
               tc_commit(a_empty + 8 * sa);
