@@ -71,6 +71,13 @@ def test_new_entry_points_validate_without_gpu():
     assert L.m4d_backproject_bwd(None, 16, 16, dim, 16, 16, None) == -1 and "null" in _lib.last_error()
     assert L.m4d_rgb_conv_dn(16, 2, 16, 16, 1, 8, 8, 16, 16, 0.1, 16, 16, None) == -1 and "bad sizes" in _lib.last_error()
     assert L.m4d_sncv_fwd_ex(16, 16, 1, 4, 4, 8, 1, 2, 16, 25, 0, None) == -1 and "search_range" in _lib.last_error()
+    # first encoder layer with the conv weights as kernel parameters: argument checks come before any device work
+    assert L.m4d_rgb_conv_dn_hostw(16, 2, 16, 16, 1, 8, 8, 16, 16, 0.1, 16, 16, None) == -1 and "bad sizes" in _lib.last_error()
+    assert L.m4d_rgb_conv_dn_hostw(16, 3, None, 16, 1, 8, 8, 16, 16, 0.1, 16, 16, None) == -1 and "null" in _lib.last_error()
+    assert L.m4d_rgb_conv_stats_hostw(16, 2, 16, 16, 1, 8, 8, 16, 16, None) == -1 and "bad sizes" in _lib.last_error()
+    assert L.m4d_rgb_conv_stats_hostw(16, 3, 16, 16, 1, 8, 8, 24, 16, None) == -1 and "16-byte aligned" in _lib.last_error()
+    assert L.m4d_domain_norm_apply(16, 1, 8, 8, 24, 16, 16, 0.1, 16, 16, None) == -1 and "c must be 16 or 32" in _lib.last_error()
+    assert L.m4d_domain_norm_apply(16, 1, 8, 8, 16, 16, 16, 0.1, None, 16, None) == -1 and "null" in _lib.last_error()
     assert L.m4d_debug_conv_profile(None) in (0, 1)
     assert L.m4d_pscv_fused_bwd(16, 16, 16, 16, 16, 4, 16, 16, 16, 1, 1, 8, 32, 2, 4, 16, 18, None, 9, 16, 16, 16, 16, None) == -1
     assert "h,w >= 2" in _lib.last_error()
