@@ -268,7 +268,9 @@ class FeaturePyramid:
                                       L.ptr(dn.scale), L.ptr(dn.bias), float(LEAKY), L.ptr(stats), L.ptr(out), L.stream()))
         return out
 
-    def call(self, images):
+    def call(self, images, on_level=None):
+        """``on_level(i, feature_map)`` (optional) is called as soon as level i's feature map has been enqueued: M4Depth uses it
+        to start the decoder's encoder-only work of that level on a side stream while the deeper encoder levels run."""
         L.f32c(images, "images")
         prev_out = images
         out_features = []
@@ -282,6 +284,8 @@ class FeaturePyramid:
                 tmp = conv1(prev_out, alpha=LEAKY)
             prev_out = conv2(tmp, alpha=LEAKY)
             out_features.append(prev_out)
+            if on_level is not None:
+                on_level(i, prev_out)
         return out_features
 
     __call__ = call
@@ -498,9 +502,24 @@ class DepthEstimatorPyramid:
                        for i in range(settings["nbre_lvls"])]
         self.is_training = settings["is_training"]
         self._cam = None
-        self.side_stream_prep = os.environ.get("M4D_SIDE_STREAM", "1") != "0"
+        # M4D_SIDE_STREAM: 0 = everything on the calling stream; 1 = fork after the encoder (one side stream); 2 (default) = the
+        # preparation of level l forks as soon as the ENCODER has produced level l (M4Depth._forward), one side stream per level
+        self.side_stream_prep = int(os.environ.get("M4D_SIDE_STREAM", "2"))
         self._side = None
         self._fork = None
+        self._lvl_side = None
+
+    def fork_prepare(self, l, f_map, new_traj):
+        """Enqueue level l's encoder-only work (DepthEstimatorLevel.prepare) on that level's side stream, behind everything
+        enqueued on the current stream so far.  The level's next ``call`` waits for it."""
+        dev = f_map.device
+        if self._lvl_side is None or self._lvl_side[0][0].device != dev:
+            self._lvl_side = [(torch.cuda.Stream(device=dev), torch.cuda.Event()) for _ in self.levels]
+        side, fork = self._lvl_side[l]
+        fork.record(torch.cuda.current_stream())
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            self.levels[l].prepare(f_map, with_sncv=not _new_traj_flag(new_traj))
 
     def call(self, f_maps_pyrs, traj_samples, camera, training=False):
         if training:
@@ -517,7 +536,7 @@ class DepthEstimatorPyramid:
         for f_pyr_curr, sample in zip(f_maps_pyrs, traj_samples):
             rot, trans, new_traj = sample['rot'], sample['trans'], sample["new_traj"]
             d_est_curr = None
-            if self.side_stream_prep:
+            if self.side_stream_prep and all(lvl._prepared is None for lvl in self.levels):
                 # Feature preparation and SNCV of every level depend on the encoder output only: fork them onto a side stream,
                 # coarse level first (the order the decoder needs them in).  Levels 6-3 are chains of small launches that leave
                 # most SMs idle; the bandwidth-bound preparation of levels 1-2 runs underneath them.  Each level's call waits
@@ -658,8 +677,11 @@ class M4Depth:
         # The recurrent state lives in the levels, so this is the same computation.  Only the last frame's maps stay valid.
         d_maps_pyrs = []
         for s in traj_samples:
+            hook = None
+            if self.d_estimator.side_stream_prep == 2:
+                hook = lambda i, fmap, s=s: self.d_estimator.fork_prepare(i, fmap, s["new_traj"])
             with _nvtx("M4Depth/encoder"):
-                pyr = self.encoder(s['RGB_im'])
+                pyr = self.encoder(s['RGB_im'], on_level=hook)
             with _nvtx("M4Depth/d_estimator"):
                 d_maps_pyrs += self.d_estimator([pyr], [s], camera, False)
         h, w = traj_samples[-1]['RGB_im'].shape[1:3]

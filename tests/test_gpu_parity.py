@@ -1264,7 +1264,7 @@ def test_model_side_stream_preparation_is_the_same_computation(graph):
     cam = dev_cam(camera_for("kitti", b, H, W))
     for abl in (None, m.M4depthAblationParameters(SNCV=False), m.M4depthAblationParameters(normalize_features=False)):
         outs = {}
-        for side in (False, True):
+        for side in (0, 1, 2):           # serial | one fork after the encoder | per-level forks from inside the encoder
             model = m.M4Depth(nbre_levels=nl, use_cuda_graph=graph, ablation_settings=abl)
             model.d_estimator.side_stream_prep = side
             wts = dict(w)
@@ -1287,8 +1287,9 @@ def test_model_side_stream_preparation_is_the_same_computation(graph):
             res += [lvl.depth_prev_t.clone() for lvl in model.d_estimator.levels]
             res += [lvl.prev_f_maps.clone() for lvl in model.d_estimator.levels]
             outs[side] = res
-        for a, bb in zip(outs[False], outs[True]):
-            assert torch.equal(a, bb)
+        for side in (1, 2):
+            for a, bb in zip(outs[0], outs[side]):
+                assert torch.equal(a, bb)
 
 
 # ----------------------------------------------------- whole model at the BASELINE.json sizes, bounded by oracle-vs-oracle
