@@ -556,6 +556,10 @@ class DepthEstimatorPyramid:
                 level = self.levels[l]
                 local_camera = {"f": self._cam[0][l], "c": self._cam[1][l]}
                 d_est = dict(d_est_curr[-1]) if d_est_curr else None
+                # a level also waits for the side-stream work of the next finer level (the largest of all: level 1's SNCV), so
+                # that the bandwidth-bound kernels of levels 1-2 on this stream do not share the machine with it
+                if l >= 1 and self.levels[l - 1]._prepared is not None:
+                    torch.cuda.current_stream().wait_event(self.levels[l - 1]._prepared["done"])
                 with _nvtx(f"DepthEstimatorLevel/{l + 1}"):
                     est = level(f_pyr_curr[l], d_est, rot, trans, local_camera, new_traj)
                 d_est_curr = [est] if d_est_curr is None else d_est_curr + [est]
